@@ -1,0 +1,119 @@
+// esb_device.cuh -- device-side data layout and helpers shared by the kernels of libesb.so.
+//
+// One CTA owns one replica: positions (+type), velocities, forces and the positions of the last
+// neighbour build live in shared memory for the whole launch; the neighbour list (full list, u16
+// indices) lives in a per-replica global arena that stays L2-resident.  See DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/esb.h"
+
+#define ESB_THREADS 256
+#define ESB_G 8                      // lanes cooperating on one atom (pair loop and list build)
+#define ESB_GROUPS (ESB_THREADS / ESB_G)
+#define ESB_MAX_TERMS 8              // bonded terms per atom (linear chain: 2 bonds + 3 angles)
+#define ESB_MAX_SPEC 8               // excluded partners per atom (linear chain: 6)
+#define ESB_NL_CHUNK 2048            // arena chunk a lane-group grabs
+#define ESB_NL_MAXNB 1023            // neighbours per atom (12-bit count in the head word)
+#define ESB_NL_POOL (256 * 1024)     // u16 entries per replica arena
+#define ESB_N_SETUPS 9               // 0 = pair soft, 1..4 = table maps 0..3 (closed form + patch), 5..8 = same maps, array lookups
+
+// One (KEY,cut) table.  plo..phi is the bin range served from the value array at poff (the
+// "patch"); outside it the closed form is evaluated at the bin midpoint.  Array-only tables are
+// expressed as plo = 0, phi = tlm1.
+struct DevTab {
+    double innersq, invdelta;   // exact bin index: int((rsq - innersq) * invdelta)
+    float cutsq;                // effective cutoff^2: beyond it every bin value is 0
+    float rcsq;                 // closed form cut-off^2
+    float K;                    // 24 eps_eff / s^6
+    float is6;                  // 1 / s^6
+    float c;                    // alpha (1-lam)^2
+    float delta;
+    int plo, phi, poff;
+    int epoff;                  // offset of the full energy array (parity hook only)
+};
+
+// Per pair-style set-up: everything indexed by ti*ESB_MAXT+tj.
+struct PairSetup {
+    float cutsq[ESB_MAXT * ESB_MAXT];       // accept test (soft: rc^2; table: effective cut^2)
+    float cutsq_skin[ESB_MAXT * ESB_MAXT];  // list test (cut+skin)^2
+    unsigned char tabid[ESB_MAXT * ESB_MAXT];
+    unsigned char range[ESB_MAXT + 4];      // cells to search on each side, per type of the central atom
+};
+
+struct Layout {
+    int gene_start, promoter_length, n_enh, n_s5p;
+};
+
+struct ReplicaScalars {       // persistent per-replica state outside the bead arrays
+    unsigned long long seed;
+    unsigned long long eval;  // force-evaluation counter = Langevin noise index
+    long long step;           // MD step
+    double r0[3];             // current bond r0 (fix adapt leaves its last value behind)
+    double soft_a;
+    int threshold;            // ser5p_to_activate
+    float p_activation;       // stored as the fp32 the device compares with (see observe)
+    double p_activation_d;
+    int gene_state, marked, delay, duration, total_active;
+    int status;
+    int pad;
+};
+
+struct KArgs {
+    int n_atoms, n_pad, n_topo, n_replicas;
+    float lo[3], hi[3];
+    float dt, gamma1, gamma2, wall_eps, wall_cut, skin_half_sq;
+    int langevin_mode;
+    float bond_k[3], angle_k[3];
+    double ramp_bond[3][2];   // ramp(v0,v1) of fix s2/s3 per bond type
+    double ramp_soft[2];
+    // cell grid
+    int ncx, ncy, ncz, ncells;
+    float cell_inv;           // 1 / cell edge
+    // device arrays
+    float4 *pos4;             // [R][n_pad] x,y,z,type bits
+    float4 *vel4;             // [R][n_pad]
+    ReplicaScalars *rs;       // [R]
+    const unsigned char *frozen;     // [n_pad]
+    const uint2 *bterm;       // [ESB_MAX_TERMS][n_topo_pad]
+    const unsigned short *spec;      // [n_topo_pad][ESB_MAX_SPEC]
+    int n_topo_pad;
+    const PairSetup *setups;  // [ESB_N_SETUPS]
+    const DevTab *tabs;       // [n_tables] (the launch picks the closed-form or the array flavour)
+    int n_tables;
+    const float *tabval;      // patch / array values (F/r), fp32
+    const float *tabe;        // energy arrays (hook)
+    int tlm1;
+    unsigned short *nl_pool;  // [R][ESB_NL_POOL]
+    unsigned int *nl_head;    // [R][n_pad]   start | count << 20
+    const esb_chunk_desc *descs;
+    // observation
+    Layout lay;
+    const int *enh_idx, *s5p_idx;
+    const double *cluster_r;  // [50]
+    double *frames;           // [R][max_chunks][9]
+    unsigned short *hist;     // [R][max_chunks][49]
+    int max_chunks;
+    unsigned long long *counters;  // [R][6]
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// u32 -> uniform in [-0.5, 0.5]; identical to the oracle's u32_to_centered.
+__device__ __forceinline__ float u32_centered(uint32_t u) { return (float)(int32_t)u * 0x1p-32f; }
+
+size_t esb_smem_bytes(int n_pad, int n_tables);

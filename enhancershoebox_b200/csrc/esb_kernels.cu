@@ -1,0 +1,769 @@
+// esb_kernels.cu -- sm_100a kernels of the EnhancerShoeBox hot path.
+//
+// esb_run_kernel      one CTA per replica; whole replica resident in shared memory; per chunk:
+//                     set-up force evaluation + n_steps x {integrate, (re)build list, forces},
+//                     then the per-chunk measurements / gene state machine / frame record.
+// esb_forces_kernel   parity hook: one force evaluation (+ energies) at the stored positions.
+// esb_pack/unpack     double <-> float4 state conversion for the host-facing ABI.
+//
+// Reference semantics (what each phase stands in for) are cited at the device functions.
+#include "esb_device.cuh"
+
+namespace {
+
+struct Smem {
+    float4 *pos;                 // x, y, z, (type | frozen << 8) as int bits
+    float *vx, *vy, *vz;
+    float *fx, *fy, *fz;         // forces; the same bytes serve as cell-list scratch during a build
+    float *bx, *by, *bz;         // positions at the last neighbour build
+    PairSetup *setup;
+    DevTab *tab;
+    int *misc;                   // see M_* below
+    double *dmisc;
+    // aliases into the force region, valid only inside build_lists()
+    unsigned short *cend;        // [ncells + 2]  inclusive prefix: end offset of every cell
+    unsigned short *sidx;        // [n_pad]       atom indices sorted by cell
+};
+
+enum { M_WORK = 0, M_WORK2, M_POOLCUR, M_FAIL, M_PAIRS, M_CURLIST, M_SCAN /* 8 warps */,
+       M_CNT_PROM = M_SCAN + 8, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */, M_END = M_HIST + 52 };
+static_assert(ESB_MAX_TERMS == ESB_G, "one bonded term per lane of a group");
+static_assert(ESB_THREADS == 256, "scan scratch assumes 8 warps");
+enum { D_RR = 0, D_PROBE = 3, D_GENE = 6, D_END = 10 };
+
+__device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+__host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables)
+{
+    size_t b = 0;
+    b += (size_t)n_pad * 16;                 // pos
+    b += (size_t)n_pad * 4 * 9;              // v, f, xbuild
+    b += (sizeof(PairSetup) + 15) & ~(size_t)15;
+    b += ((size_t)n_tables * sizeof(DevTab) + 15) & ~(size_t)15;
+    b += (size_t)M_END * 4;
+    b += (size_t)D_END * 8;
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ void carve(unsigned char *base, const KArgs &a, Smem &S)
+{
+    const int np = a.n_pad;
+    size_t o = 0;
+    S.pos = reinterpret_cast<float4 *>(base + o); o += (size_t)np * 16;
+    S.vx = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.vy = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.vz = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.fx = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.fy = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.fz = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.bx = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.by = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.bz = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.setup = reinterpret_cast<PairSetup *>(base + o); o += align16(sizeof(PairSetup));
+    S.tab = reinterpret_cast<DevTab *>(base + o); o += align16((size_t)a.n_tables * sizeof(DevTab));
+    S.dmisc = reinterpret_cast<double *>(base + o); o += (size_t)D_END * 8;
+    S.misc = reinterpret_cast<int *>(base + o);
+    S.cend = reinterpret_cast<unsigned short *>(S.fx);
+    S.sidx = S.cend + ((a.ncells + 2 + 7) & ~7);
+}
+
+__device__ __forceinline__ void load_setup(const Smem &S, const KArgs &a, int setup_id)
+{
+    const int *src = reinterpret_cast<const int *>(a.setups + setup_id);
+    int *dst = reinterpret_cast<int *>(S.setup);
+    for (int k = threadIdx.x; k < (int)(sizeof(PairSetup) / 4); k += ESB_THREADS) dst[k] = src[k];
+}
+
+__device__ __forceinline__ int cell_coord(float x, float lo, float inv, int n)
+{
+    int c = (int)((x - lo) * inv);
+    return min(max(c, 0), n - 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Neighbour list build.  Stands in for LAMMPS' binned neighbour build (`neighbor 0.3 multi`,
+// `neigh_modify every 1 delay 10 check yes`, run_single_shoebox.py:532-533): per-type-pair
+// cutoff + skin, 1-2/1-3/1-4 partners excluded (default special_bonds).  Full list (both i->j and
+// j->i) so the force loop needs no scatter.  Deterministic: cells are sorted by atom index.
+// ------------------------------------------------------------------------------------------------
+__device__ void build_lists(const Smem &S, const KArgs &a, int r)
+{
+    const int tid = threadIdx.x, n = a.n_atoms;
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned int *cw = reinterpret_cast<unsigned int *>(S.cend);
+    const int ncw = (a.ncells + 2 + 1) >> 1;
+    for (int w = tid; w < ncw; w += ESB_THREADS) cw[w] = 0u;
+    if (tid == 0) { S.misc[M_WORK2] = 0; S.misc[M_POOLCUR] = 0; S.misc[M_CURLIST] = 0; }
+    __syncthreads();
+    // count (cell c is stored at slot c+1 so that, after the scan, slot c holds start(c))
+    for (int i = tid; i < n; i += ESB_THREADS) {
+        const float4 p = S.pos[i];
+        S.bx[i] = p.x; S.by[i] = p.y; S.bz[i] = p.z;
+        const int cx = cell_coord(p.x, a.lo[0], a.cell_inv, a.ncx);
+        const int cy = cell_coord(p.y, a.lo[1], a.cell_inv, a.ncy);
+        const int cz = cell_coord(p.z, a.lo[2], a.cell_inv, a.ncz);
+        const int slot = (cz * a.ncy + cy) * a.ncx + cx + 1;
+        atomicAdd(&cw[slot >> 1], 1u << (16 * (slot & 1)));
+    }
+    __syncthreads();
+    // inclusive scan over slots 0..ncells (slot 0 is 0): afterwards cend[c] = start of cell c
+    {
+        const int total = a.ncells + 1;
+        const int per = (total + ESB_THREADS - 1) / ESB_THREADS;
+        const int b0 = min(tid * per, total), b1 = min(b0 + per, total);
+        int sum = 0;
+        for (int c = b0; c < b1; c++) sum += S.cend[c];
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) S.misc[M_SCAN + warp] = incl;
+        __syncthreads();
+        int base = incl - sum;
+        for (int w = 0; w < warp; w++) base += S.misc[M_SCAN + w];
+        for (int c = b0; c < b1; c++) { base += S.cend[c]; S.cend[c] = (unsigned short)base; }
+    }
+    __syncthreads();
+    // scatter: cend[c] (= start of c) is used as the cursor of cell c; afterwards cend[c] = end of c
+    for (int i = tid; i < n; i += ESB_THREADS) {
+        const float4 p = S.pos[i];
+        const int cx = cell_coord(p.x, a.lo[0], a.cell_inv, a.ncx);
+        const int cy = cell_coord(p.y, a.lo[1], a.cell_inv, a.ncy);
+        const int cz = cell_coord(p.z, a.lo[2], a.cell_inv, a.ncz);
+        const int slot = (cz * a.ncy + cy) * a.ncx + cx;
+        const unsigned int old = atomicAdd(&cw[slot >> 1], 1u << (16 * (slot & 1)));
+        S.sidx[(old >> (16 * (slot & 1))) & 0xffffu] = (unsigned short)i;
+    }
+    __syncthreads();
+    // order every cell by atom index (insertion sort; cells hold a handful of beads)
+    for (int c = tid; c < a.ncells; c += ESB_THREADS) {
+        const int s0 = c ? S.cend[c - 1] : 0, s1 = S.cend[c];
+        for (int p = s0 + 1; p < s1; p++) {
+            const unsigned short v = S.sidx[p];
+            int q = p - 1;
+            while (q >= s0 && S.sidx[q] > v) { S.sidx[q + 1] = S.sidx[q]; q--; }
+            S.sidx[q + 1] = v;
+        }
+    }
+    __syncthreads();
+
+    const int gl = tid & (ESB_G - 1);
+    const int gshift = lane & ~(ESB_G - 1);
+    const unsigned int gmask = ((1u << ESB_G) - 1u) << gshift;
+    unsigned short *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
+    unsigned int *head = a.nl_head + (size_t)r * a.n_pad;
+    int cursor = 0, limit = 0;
+    unsigned int listed = 0;
+    for (;;) {
+        int idx = 0;
+        if (gl == 0) idx = atomicAdd(&S.misc[M_WORK2], 1);
+        idx = __shfl_sync(gmask, idx, gshift);
+        if (idx >= n) break;
+        const int i = n - 1 - idx;
+        if (limit - cursor < ESB_NL_MAXNB + 1) {
+            int c = 0;
+            if (gl == 0) c = atomicAdd(&S.misc[M_POOLCUR], ESB_NL_CHUNK);
+            c = __shfl_sync(gmask, c, gshift);
+            if (c + ESB_NL_CHUNK > ESB_NL_POOL) {
+                if (gl == 0) { atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH); head[i] = 0u; }
+                continue;
+            }
+            cursor = c; limit = c + ESB_NL_CHUNK;
+        }
+        const float4 pi = S.pos[i];
+        const int ti = __float_as_int(pi.w) & 0xff;
+        const int rng = S.setup->range[ti];
+        const int cx = cell_coord(pi.x, a.lo[0], a.cell_inv, a.ncx);
+        const int cy = cell_coord(pi.y, a.lo[1], a.cell_inv, a.ncy);
+        const int cz = cell_coord(pi.z, a.lo[2], a.cell_inv, a.ncz);
+        const int x0 = max(cx - rng, 0), x1 = min(cx + rng, a.ncx - 1);
+        const int y0 = max(cy - rng, 0), y1 = min(cy + rng, a.ncy - 1);
+        const int z0 = max(cz - rng, 0), z1 = min(cz + rng, a.ncz - 1);
+        const bool topo_i = i < a.n_topo;
+        uint4 sp = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (topo_i) sp = *reinterpret_cast<const uint4 *>(a.spec + (size_t)i * ESB_MAX_SPEC);
+        const float *cs = S.setup->cutsq_skin + ti * ESB_MAXT;
+        int cnt = 0;
+        for (int z = z0; z <= z1; z++)
+            for (int y = y0; y <= y1; y++) {
+                const int row = (z * a.ncy + y) * a.ncx;
+                const int ka = (row + x0) ? S.cend[row + x0 - 1] : 0;
+                const int kb = S.cend[row + x1];
+                for (int k0 = ka; k0 < kb; k0 += ESB_G) {
+                    const int k = k0 + gl;
+                    bool ok = false;
+                    int j = 0;
+                    if (k < kb) {
+                        j = S.sidx[k];
+                        const float4 pj = S.pos[j];
+                        const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                        const float r2 = dx * dx + dy * dy + dz * dz;
+                        const int tj = __float_as_int(pj.w) & 0xff;
+                        ok = (r2 < cs[tj]) && (j != i);
+                        if (ok && topo_i && j < a.n_topo) {
+                            const unsigned int jj = (unsigned int)j;
+                            ok = !((sp.x & 0xffffu) == jj || (sp.x >> 16) == jj || (sp.y & 0xffffu) == jj || (sp.y >> 16) == jj ||
+                                   (sp.z & 0xffffu) == jj || (sp.z >> 16) == jj || (sp.w & 0xffffu) == jj || (sp.w >> 16) == jj);
+                        }
+                    }
+                    const unsigned int bits = (__ballot_sync(gmask, ok) >> gshift) & ((1u << ESB_G) - 1u);
+                    if (ok) {
+                        const int slot = cnt + __popc(bits & ((1u << gl) - 1u));
+                        if (slot < ESB_NL_MAXNB) pool[cursor + slot] = (unsigned short)j;
+                    }
+                    cnt += __popc(bits);
+                }
+            }
+        if (cnt > ESB_NL_MAXNB) {
+            if (gl == 0) atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH);
+            cnt = ESB_NL_MAXNB;
+        }
+        if (gl == 0) { head[i] = (unsigned int)cursor | ((unsigned int)cnt << 20); listed += cnt; }
+        cursor += cnt;
+    }
+    if (listed) atomicAdd(&S.misc[M_CURLIST], (int)listed);
+    __syncthreads();   // lists (global) and the scratch alias are settled before forces are written
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bonded terms of one atom (gathered per atom so that no force is ever scattered):
+// [LAMMPS-ext] BondHarmonic::compute  E = K (r - r0)^2       (bond_coeff, run_single_shoebox.py:632-633)
+// [LAMMPS-ext] AngleCosine::compute   E = K (1 + cos theta)  (angle_coeff, run_single_shoebox.py:583-584)
+// ------------------------------------------------------------------------------------------------
+template <bool ENERGY>
+__device__ __forceinline__ void bonded_term(const Smem &S, const KArgs &a, const float4 pi, uint2 term,
+                                            const float r0_1, const float r0_2,
+                                            float &fx, float &fy, float &fz, double &e_bond, double &e_angle)
+{
+    const int kind = term.y & 0xff, type = (term.y >> 8) & 0xff;
+    if (kind == 0) return;
+    const float4 pa = S.pos[term.x & 0xffffu];
+    if (kind == 1) {
+        const float dx = pi.x - pa.x, dy = pi.y - pa.y, dz = pi.z - pa.z;
+        const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+        const float dr = r - (type == 1 ? r0_1 : r0_2);
+        const float rk = a.bond_k[type] * dr;
+        const float fb = (r > 0.0f) ? -2.0f * rk / r : 0.0f;
+        fx += dx * fb; fy += dy * fb; fz += dz * fb;
+        if (ENERGY) e_bond += 0.5 * (double)(rk * dr);   // each bond is visited from both ends
+        return;
+    }
+    const float4 pb = S.pos[term.x >> 16];
+    const float k = a.angle_k[type];
+    if (kind == 2) {
+        // this atom is an end (i1); pa = vertex (i2), pb = other end (i3)
+        const float d1x = pi.x - pa.x, d1y = pi.y - pa.y, d1z = pi.z - pa.z;
+        const float d2x = pb.x - pa.x, d2y = pb.y - pa.y, d2z = pb.z - pa.z;
+        const float rsq1 = d1x * d1x + d1y * d1y + d1z * d1z, rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
+        const float r1r2 = sqrtf(rsq1) * sqrtf(rsq2);
+        float c = (d1x * d2x + d1y * d2y + d1z * d2z) / r1r2;
+        c = fminf(fmaxf(c, -1.0f), 1.0f);
+        const float a11 = k * c / rsq1, a12 = -k / r1r2;
+        fx += a11 * d1x + a12 * d2x; fy += a11 * d1y + a12 * d2y; fz += a11 * d1z + a12 * d2z;
+    } else {
+        // this atom is the vertex (i2); pa = i1, pb = i3
+        const float d1x = pa.x - pi.x, d1y = pa.y - pi.y, d1z = pa.z - pi.z;
+        const float d2x = pb.x - pi.x, d2y = pb.y - pi.y, d2z = pb.z - pi.z;
+        const float rsq1 = d1x * d1x + d1y * d1y + d1z * d1z, rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
+        const float r1r2 = sqrtf(rsq1) * sqrtf(rsq2);
+        float c = (d1x * d2x + d1y * d2y + d1z * d2z) / r1r2;
+        c = fminf(fmaxf(c, -1.0f), 1.0f);
+        const float a11 = k * c / rsq1, a12 = -k / r1r2, a22 = k * c / rsq2;
+        fx -= (a11 * d1x + a12 * d2x) + (a22 * d2x + a12 * d1x);
+        fy -= (a11 * d1y + a12 * d2y) + (a22 * d2y + a12 * d1y);
+        fz -= (a11 * d1z + a12 * d2z) + (a22 * d2z + a12 * d1z);
+        if (ENERGY) e_angle += (double)(k * (1.0f + c));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Force evaluation: pair (soft or tabulated) + bonded, gathered per atom by a group of ESB_G lanes.
+//
+// MODE 1  [LAMMPS-ext] PairSoft::compute   E = A [1 + cos(pi r / rc)]   (run_single_shoebox.py:589-628)
+// MODE 2  [LAMMPS-ext] PairTable::compute, tabstyle LOOKUP: itable = int((rsq - innersq) * invdelta),
+//         fpair = f[itable] (run_single_shoebox.py:800-874).  The bin index is computed in fp64 from
+//         the fp32 coordinates with the same (unfused) operations as the oracle, so it is bit-exact;
+//         the bin value comes from the LOOKUP array inside the table's patch range and from the
+//         LJsoft closed form evaluated at the bin midpoint outside it (ljsoft_potential.py:10-16).
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool ENERGY>
+__device__ void force_phase(const Smem &S, const KArgs &a, int r, const float soft_a, const float r0_1, const float r0_2,
+                            double *energy /* [3] pair, bond, angle: per-thread partials (ENERGY only) */)
+{
+    const int tid = threadIdx.x, n = a.n_atoms;
+    const int lane = tid & 31;
+    const int gl = tid & (ESB_G - 1);
+    const int gshift = lane & ~(ESB_G - 1);
+    const unsigned int gmask = ((1u << ESB_G) - 1u) << gshift;
+    const unsigned short *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
+    const unsigned int *head = a.nl_head + (size_t)r * a.n_pad;
+    unsigned int npairs = 0;
+    double e_pair = 0.0, e_bond = 0.0, e_angle = 0.0;
+    for (;;) {
+        int idx = 0;
+        if (gl == 0) idx = atomicAdd(&S.misc[M_WORK], 1);
+        idx = __shfl_sync(gmask, idx, gshift);
+        if (idx >= n) break;
+        const int i = n - 1 - idx;
+        const float4 pi = S.pos[i];
+        const int ti = __float_as_int(pi.w) & 0xff;
+        const unsigned int h = head[i];
+        const unsigned short *nl = pool + (h & 0xfffffu);
+        const int cnt = (int)(h >> 20);
+        const float *cutsq = S.setup->cutsq + ti * ESB_MAXT;
+        const unsigned char *tabid = S.setup->tabid + ti * ESB_MAXT;
+        const double xid = (double)pi.x, yid = (double)pi.y, zid = (double)pi.z;
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        for (int e = gl; e < cnt; e += ESB_G) {
+            const int j = nl[e];
+            const float4 pj = S.pos[j];
+            const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+            const float r2 = dx * dx + dy * dy + dz * dz;
+            const int tj = __float_as_int(pj.w) & 0xff;
+            if (r2 < cutsq[tj]) {
+                float fpair;
+                if (MODE == 1) {
+                    const float rc = sqrtf(cutsq[tj]);
+                    const float rr = sqrtf(r2);
+                    const float arg = 3.14159265358979323846f * rr / rc;
+                    fpair = (rr > 0.0f) ? soft_a * sinf(arg) * 3.14159265358979323846f / rc / rr : 0.0f;
+                    if (ENERGY) e_pair += 0.5 * (double)(soft_a * (1.0f + cosf(arg)));
+                } else {
+                    const DevTab &T = S.tab[tabid[tj]];
+                    const double ddx = __dsub_rn(xid, (double)pj.x), ddy = __dsub_rn(yid, (double)pj.y), ddz = __dsub_rn(zid, (double)pj.z);
+                    const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
+                    if (rsq < T.innersq) { atomicOr(&S.misc[M_FAIL], ESB_ST_INNER); continue; }
+                    const int it = (int)__dmul_rn(__dsub_rn(rsq, T.innersq), T.invdelta);
+                    if (it >= T.plo && it < T.phi) {
+                        fpair = a.tabval[T.poff + it];
+                    } else {
+                        const float q = (float)T.innersq + ((float)it + 0.5f) * T.delta;
+                        if (q < T.rcsq) {
+                            const float q2 = q * q;
+                            const float x = fmaf(q2 * q, T.is6, T.c);
+                            const float inv = __frcp_rn(x);
+                            fpair = T.K * q2 * (2.0f - x) * (inv * inv * inv);
+                        } else {
+                            fpair = 0.0f;
+                        }
+                    }
+                    if (ENERGY) e_pair += 0.5 * (double)a.tabe[T.epoff + min(it, a.tlm1 - 1)];
+                }
+                fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+                npairs++;
+            }
+        }
+        if (i < a.n_topo) {
+            const uint2 term = a.bterm[(size_t)gl * a.n_topo_pad + i];
+            bonded_term<ENERGY>(S, a, pi, term, r0_1, r0_2, fx, fy, fz, e_bond, e_angle);
+        }
+#pragma unroll
+        for (int d = ESB_G >> 1; d >= 1; d >>= 1) {
+            fx += __shfl_xor_sync(gmask, fx, d);
+            fy += __shfl_xor_sync(gmask, fy, d);
+            fz += __shfl_xor_sync(gmask, fz, d);
+        }
+        if (gl == 0) { S.fx[i] = fx; S.fy[i] = fy; S.fz[i] = fz; }
+    }
+    if (npairs) atomicAdd(&S.misc[M_PAIRS], (int)npairs);
+    if (ENERGY) { energy[0] += e_pair; energy[1] += e_bond; energy[2] += e_angle; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// post_force fixes of one atom, in the order the reference creates them
+// (run_single_shoebox.py:643-671): langevin -> wall/harmonic x6 -> setforce on the anchors.
+// [LAMMPS-ext] FixLangevin::post_force (uniform noise), FixWallHarmonic::wall_particle, FixSetForce.
+// ------------------------------------------------------------------------------------------------
+template <bool ENERGY>
+__device__ __forceinline__ int post_force(const KArgs &a, int i, const float4 p, const float vx, const float vy, const float vz,
+                                          float &fx, float &fy, float &fz, const uint32_t k0, const uint32_t k1,
+                                          const unsigned long long eval, double &e_wall)
+{
+    int fail = 0;
+    if (a.langevin_mode) {
+        float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+        if (a.langevin_mode == 1) {
+            uint32_t o[4];
+            philox4x32_10((uint32_t)i, (uint32_t)eval, (uint32_t)(eval >> 32), 0u, k0, k1, o);
+            nx = u32_centered(o[0]); ny = u32_centered(o[1]); nz = u32_centered(o[2]);
+        }
+        fx += a.gamma1 * vx + a.gamma2 * nx;
+        fy += a.gamma1 * vy + a.gamma2 * ny;
+        fz += a.gamma1 * vz + a.gamma2 * nz;
+    }
+#define ESB_WALL(X, LO, HI, F)                                                                          \
+    {                                                                                                   \
+        const float dlo = (X) - (LO), dhi = (HI) - (X);                                                 \
+        if (dlo < a.wall_cut) {                                                                         \
+            if (!(dlo > 0.0f)) fail = ESB_ST_WALL;                                                      \
+            else { const float dr = a.wall_cut - dlo; (F) += 2.0f * a.wall_eps * dr; if (ENERGY) e_wall += (double)(a.wall_eps * dr * dr); } \
+        }                                                                                               \
+        if (dhi < a.wall_cut) {                                                                         \
+            if (!(dhi > 0.0f)) fail = ESB_ST_WALL;                                                      \
+            else { const float dr = a.wall_cut - dhi; (F) -= 2.0f * a.wall_eps * dr; if (ENERGY) e_wall += (double)(a.wall_eps * dr * dr); } \
+        }                                                                                               \
+        if (!(dlo == dlo)) fail = ESB_ST_NONFINITE;                                                     \
+    }
+    ESB_WALL(p.x, a.lo[0], a.hi[0], fx)
+    ESB_WALL(p.y, a.lo[1], a.hi[1], fy)
+    ESB_WALL(p.z, a.lo[2], a.hi[2], fz)
+#undef ESB_WALL
+    if (__float_as_int(p.w) & 0x100) { fx = 0.0f; fy = 0.0f; fz = 0.0f; }
+    if (!(fx == fx) || !(fy == fy) || !(fz == fz)) fail |= ESB_ST_NONFINITE;
+    return fail;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-atom update between two force evaluations.
+// [LAMMPS-ext] FixNVE: final_integrate of step n (v += dt/2 f) and initial_integrate of step n+1
+// (v += dt/2 f; x += dt v) are adjacent per-atom operations and are fused here
+// (fix 1 all nve, timestep 0.005: run_single_shoebox.py:643, 680).
+// Returns (rebuild needed) | (failure bits << 1).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int atom_phase(const Smem &S, const KArgs &a, const bool do_final, const bool do_initial,
+                                          const uint32_t k0, const uint32_t k1, const unsigned long long eval)
+{
+    int flags = 0;
+    const float dtf = 0.5f * a.dt, dtv = a.dt;
+    double dummy = 0.0;
+    for (int i = threadIdx.x; i < a.n_atoms; i += ESB_THREADS) {
+        float4 p = S.pos[i];
+        float vx = S.vx[i], vy = S.vy[i], vz = S.vz[i];
+        float fx = S.fx[i], fy = S.fy[i], fz = S.fz[i];
+        const int fail = post_force<false>(a, i, p, vx, vy, vz, fx, fy, fz, k0, k1, eval, dummy);
+        flags |= fail << 1;
+        if (do_final) { vx += dtf * fx; vy += dtf * fy; vz += dtf * fz; }
+        if (do_initial) {
+            vx += dtf * fx; vy += dtf * fy; vz += dtf * fz;
+            p.x += dtv * vx; p.y += dtv * vy; p.z += dtv * vz;
+            S.pos[i] = p;
+            const float ex = p.x - S.bx[i], ey = p.y - S.by[i], ez = p.z - S.bz[i];
+            if (ex * ex + ey * ey + ez * ez > a.skin_half_sq) flags |= 1;
+        }
+        S.vx[i] = vx; S.vy[i] = vy; S.vz[i] = vz;
+    }
+    return flags;
+}
+
+// [LAMMPS-ext] Variable ramp(x,y) = x + (y-x)*(step-start)/(stop-start), evaluated by fix adapt
+// at set-up and every nevery steps (run_single_shoebox.py:627-639).
+__device__ __forceinline__ double ramp(const double v0, const double v1, long long step, long long rb, long long re)
+{
+    return v0 + (v1 - v0) * (double)(step - rb) / (double)(re - rb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// What the drivers do between two `run` commands, on the device (run_single_shoebox.py:913-961,
+// 1304-1400, 1457-1519 == VGM/run_single_GENES_STAGES.py:822-865, 871-978, 1033-1089).
+// All arithmetic that decides a count or ends up in geneTrack.txt is fp64 with unfused
+// multiply/add in numpy's / scipy's evaluation order, so that given the same coordinates the
+// record is bit-identical to the reference expressions.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dist_sq3(const double ax, const double ay, const double az, const float4 q)
+{
+    const double dx = __dsub_rn(ax, (double)q.x), dy = __dsub_rn(ay, (double)q.y), dz = __dsub_rn(az, (double)q.z);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__device__ void observe(const Smem &S, const KArgs &a, int r, const esb_chunk_desc &d, ReplicaScalars &rs, double delt, double sig_nm)
+{
+    const int tid = threadIdx.x;
+    const Layout L = a.lay;
+    const int probe = L.gene_start - L.promoter_length + 2;
+    for (int k = tid; k < 4 + ESB_N_SHELL; k += ESB_THREADS) S.misc[M_CNT_PROM + k] = 0;
+    if (tid == 0) {
+        // RRPosition = np.mean(atomPositions[regulatory_atoms], axis=0)   (:932)
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (int k = 0; k < L.n_enh; k++) {
+            const float4 q = S.pos[a.enh_idx[k]];
+            sx = __dadd_rn(sx, (double)q.x); sy = __dadd_rn(sy, (double)q.y); sz = __dadd_rn(sz, (double)q.z);
+        }
+        const double ne = (double)L.n_enh;
+        S.dmisc[D_RR] = __ddiv_rn(sx, ne); S.dmisc[D_RR + 1] = __ddiv_rn(sy, ne); S.dmisc[D_RR + 2] = __ddiv_rn(sz, ne);
+        const float4 pp = S.pos[probe], pg = S.pos[L.gene_start];
+        S.dmisc[D_PROBE] = pp.x; S.dmisc[D_PROBE + 1] = pp.y; S.dmisc[D_PROBE + 2] = pp.z;
+        S.dmisc[D_GENE] = pg.x; S.dmisc[D_GENE + 1] = pg.y; S.dmisc[D_GENE + 2] = pg.z;
+    }
+    __syncthreads();
+    {
+        const double px = S.dmisc[D_PROBE], py = S.dmisc[D_PROBE + 1], pz = S.dmisc[D_PROBE + 2];
+        const double gx = S.dmisc[D_GENE], gy = S.dmisc[D_GENE + 1], gz = S.dmisc[D_GENE + 2];
+        int c_prom = 0, c_gene = 0;
+        for (int k = tid; k < L.n_s5p; k += ESB_THREADS) {
+            const float4 q = S.pos[a.s5p_idx[k]];
+            // ds = cdist(PromoterPositions, ser5p_positions); IPs = ds < pol2release_radius   (:948-954)
+            if (__dsqrt_rn(dist_sq3(px, py, pz, q)) < 3.0) c_prom++;
+            if (__dsqrt_rn(dist_sq3(gx, gy, gz, q)) < 3.0) c_gene++;
+            // min distance to any enhancer bead, binned on cluster_r (:1504-1519)
+            const double qx = (double)q.x, qy = (double)q.y, qz = (double)q.z;
+            double dmin = 1e300;
+            for (int e = 0; e < L.n_enh; e++) dmin = fmin(dmin, dist_sq3(qx, qy, qz, S.pos[a.enh_idx[e]]));
+            const double dm = __dsqrt_rn(dmin);
+            int k0 = ESB_N_SHELL;
+            for (int c = 0; c < ESB_N_SHELL; c++) if (dm < a.cluster_r[c]) { k0 = c; break; }
+            if (k0 >= 1 && k0 < ESB_N_SHELL) atomicAdd(&S.misc[M_HIST + k0 - 1], 1);
+        }
+        if (c_prom) atomicAdd(&S.misc[M_CNT_PROM], c_prom);
+        if (c_gene) atomicAdd(&S.misc[M_CNT_GENE], c_gene);
+        int nrnp = 0, nrbp = 0;
+        for (int i = tid; i < a.n_atoms; i += ESB_THREADS) {
+            const int t = __float_as_int(S.pos[i].w) & 0xff;
+            nrnp += (t == 5); nrbp += (t == 4);
+        }
+        if (nrnp) atomicAdd(&S.misc[M_NRNP], nrnp);
+        if (nrbp) atomicAdd(&S.misc[M_NRBP], nrbp);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int i = d.chunk_index;
+        const int g = L.gene_start, p = L.promoter_length;
+        const double rx = S.dmisc[D_RR], ry = S.dmisc[D_RR + 1], rz = S.dmisc[D_RR + 2];
+        // d_rg (:934)
+        const double d_rg = __dsqrt_rn(dist_sq3(rx, ry, rz, S.pos[g]));
+        // d_rp: distance to the mean of the promoter beads g-1, g-2, ..., g-p (:946)
+        double mx = 0.0, my = 0.0, mz = 0.0;
+        for (int k = 0; k < p; k++) {
+            const float4 q = S.pos[g - 1 - k];
+            mx = __dadd_rn(mx, (double)q.x); my = __dadd_rn(my, (double)q.y); mz = __dadd_rn(mz, (double)q.z);
+        }
+        mx = __ddiv_rn(mx, (double)p); my = __ddiv_rn(my, (double)p); mz = __ddiv_rn(mz, (double)p);
+        const double ex = __dsub_rn(rx, mx), ey = __dsub_rn(ry, my), ez = __dsub_rn(rz, mz);
+        const double d_rp = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)));
+        const int n_prom = S.misc[M_CNT_PROM], n_gene = S.misc[M_CNT_GENE];
+
+        // --- gene state machine (:956-961, 1304-1400) ---
+        auto set_types = [&](int first, int count, int t) {
+            for (int k = 0; k < count; k++) {
+                float4 q = S.pos[first + k];
+                q.w = __int_as_float((__float_as_int(q.w) & ~0xff) | t);
+                S.pos[first + k] = q;
+            }
+        };
+        const bool on = i >= 150;  // t_induction_on == t_activation_on (:472-475)
+        if (rs.gene_state == 2) { rs.duration++; rs.total_active++; }
+        if (on && rs.gene_state == 0) { set_types(g, 5, 6); rs.gene_state = 1; }
+        if (on && rs.gene_state == 1 && n_prom > rs.threshold) {
+            uint32_t o[4];
+            philox4x32_10((uint32_t)i, 0u, 0u, 1u, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), o);
+            const double u = (double)(o[0] >> 8) * 0x1p-24;
+            if (!(u > rs.p_activation_d)) { rs.marked = 1; rs.delay = 0; rs.gene_state = 2; }
+        }
+        if (rs.marked) {
+            if (rs.delay < 2) rs.delay++;
+            else { rs.marked = 0; set_types(g, 5, 7); set_types(g - p, p, 11); }
+        }
+        if (on && rs.gene_state == 2 && rs.duration >= 50) {
+            rs.duration = 0; set_types(g, 5, 2); set_types(g - p, p, 10); rs.gene_state = 0;
+        }
+        // --- RBP -> RNP ramp (:1457-1470) ---
+        if (d.expected_rnp >= 0) {
+            int actual = S.misc[M_NRNP], nrbp = S.misc[M_NRBP];
+            uint32_t m = 0;
+            while (d.expected_rnp > actual && nrbp > 0) {
+                uint32_t o[4];
+                philox4x32_10((uint32_t)i, m, 0u, 2u, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), o);
+                int k = (int)(((unsigned long long)(o[0] >> 8) * (unsigned long long)nrbp) >> 24);
+                for (int q = 0; q < a.n_atoms; q++) {
+                    if ((__float_as_int(S.pos[q].w) & 0xff) == 4) {
+                        if (k == 0) { set_types(q, 1, 5); break; }
+                        k--;
+                    }
+                }
+                actual++; nrbp--; m++;
+            }
+        }
+        // --- geneTrack record (:1496) ---
+        if (i < a.max_chunks) {
+            double *f = a.frames + ((size_t)r * a.max_chunks + i) * ESB_FRAME_DOUBLES;
+            f[0] = __dmul_rn((double)(i + 1), delt);
+            f[1] = __dmul_rn(S.dmisc[D_PROBE], sig_nm);
+            f[2] = __dmul_rn(S.dmisc[D_PROBE + 1], sig_nm);
+            f[3] = __dmul_rn(S.dmisc[D_PROBE + 2], sig_nm);
+            f[4] = __dmul_rn(d_rp, sig_nm);
+            f[5] = __dmul_rn(d_rg, sig_nm);
+            f[6] = (double)n_prom;
+            f[7] = (double)n_gene;
+            f[8] = (double)rs.gene_state;
+        }
+    }
+    if (d.chunk_index < a.max_chunks && a.hist)
+        for (int k = tid; k < ESB_N_SHELL - 1; k += ESB_THREADS)
+            a.hist[((size_t)r * a.max_chunks + d.chunk_index) * (ESB_N_SHELL - 1) + k] = (unsigned short)S.misc[M_HIST + k];
+    __syncthreads();
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" __global__ void __launch_bounds__(ESB_THREADS, 3)
+esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const double delt, const double sig_nm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem S;
+    carve(smem_raw, a, S);
+    const int r = blockIdx.x, tid = threadIdx.x;
+    ReplicaScalars rs = a.rs[r];
+    if (rs.status != 0) return;   // a failed replica no longer advances (LAMMPS would have aborted)
+
+    for (int k = tid; k < a.n_pad; k += ESB_THREADS) {
+        S.pos[k] = a.pos4[(size_t)r * a.n_pad + k];
+        const float4 v = a.vel4[(size_t)r * a.n_pad + k];
+        S.vx[k] = v.x; S.vy[k] = v.y; S.vz[k] = v.z;
+    }
+    for (int k = tid; k < a.n_tables * (int)(sizeof(DevTab) / 4); k += ESB_THREADS)
+        reinterpret_cast<int *>(S.tab)[k] = reinterpret_cast<const int *>(a.tabs)[k];
+    for (int k = tid; k < M_END; k += ESB_THREADS) S.misc[k] = 0;
+    const uint32_t k0 = (uint32_t)rs.seed, k1 = (uint32_t)(rs.seed >> 32);
+    unsigned long long n_evals = 0, n_builds = 0, n_steps_done = 0, n_pairs = 0, n_listed = 0;
+    int failed = 0;
+
+    for (int c = chunk_begin; c < chunk_begin + n_chunks && !failed; c++) {
+        const esb_chunk_desc d = a.descs[c];
+        __syncthreads();
+        load_setup(S, a, d.pair_mode == 1 ? 0 : 1 + d.map_id);
+        // ---- Verlet::setup: fix adapt, neighbour build, one force evaluation ----
+        const long long first = rs.step, last = rs.step + d.n_steps;
+        const long long rb = d.ramp_on ? d.ramp_start : first;
+        const long long re = d.ramp_on ? d.ramp_stop : last;
+        if (d.adapt_soft) rs.soft_a = ramp(a.ramp_soft[0], a.ramp_soft[1], rs.step, rb, re);
+        if (d.adapt_bond1) rs.r0[1] = ramp(a.ramp_bond[1][0], a.ramp_bond[1][1], rs.step, rb, re);
+        if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
+        if (tid == 0) S.misc[M_WORK] = 0;
+        __syncthreads();
+        build_lists(S, a, r);
+        n_builds++;
+        if (d.pair_mode == 1) force_phase<1, false>(S, a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
+        else force_phase<2, false>(S, a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
+        n_evals++;
+        __syncthreads();
+        n_listed += (unsigned int)S.misc[M_CURLIST];
+        for (int it = 0; it <= d.n_steps; it++) {
+            const bool last_pass = (it == d.n_steps);
+            int flags = atom_phase(S, a, it > 0, !last_pass, k0, k1, rs.eval);
+            rs.eval++;
+            if (tid == 0) S.misc[M_WORK] = 0;
+            flags |= S.misc[M_FAIL] << 1;
+            flags = __syncthreads_or(flags);
+            if (flags >> 1) { failed = flags >> 1; break; }
+            if (last_pass) break;
+            rs.step++;
+            n_steps_done++;
+            if (d.adapt_soft) rs.soft_a = ramp(a.ramp_soft[0], a.ramp_soft[1], rs.step, rb, re);
+            if (rs.step % 10 == 0) {
+                if (d.adapt_bond1) rs.r0[1] = ramp(a.ramp_bond[1][0], a.ramp_bond[1][1], rs.step, rb, re);
+                if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
+            }
+            if (flags & 1) { build_lists(S, a, r); n_builds++; }
+            if (d.pair_mode == 1) force_phase<1, false>(S, a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
+            else force_phase<2, false>(S, a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
+            n_evals++;
+            __syncthreads();
+            n_listed += (unsigned int)S.misc[M_CURLIST];
+        }
+        n_pairs += (unsigned int)S.misc[M_PAIRS];
+        __syncthreads();
+        if (tid == 0) S.misc[M_PAIRS] = 0;
+        if (failed) break;
+        if (d.observe) observe(S, a, r, d, rs, delt, sig_nm);
+    }
+    __syncthreads();
+    failed |= S.misc[M_FAIL];
+    for (int k = tid; k < a.n_pad; k += ESB_THREADS) {
+        a.pos4[(size_t)r * a.n_pad + k] = S.pos[k];
+        a.vel4[(size_t)r * a.n_pad + k] = make_float4(S.vx[k], S.vy[k], S.vz[k], 0.0f);
+    }
+    if (tid == 0) {
+        rs.status |= failed;
+        a.rs[r] = rs;
+        unsigned long long *cn = a.counters + (size_t)r * 6;
+        cn[0] += n_evals; cn[1] += n_builds;
+        cn[2] += n_pairs;
+        cn[3] += n_listed;
+        cn[4] += n_steps_done;
+        cn[5] = (unsigned long long)rs.total_active;
+    }
+}
+
+// Parity hook: one force evaluation at the stored positions (esb_forces()).
+extern "C" __global__ void __launch_bounds__(ESB_THREADS, 2)
+esb_forces_kernel(const KArgs a, const int pair_mode, const int setup_id, const float soft_a, const int with_post,
+                  const unsigned long long eval, double *f_out, double *e_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem S;
+    carve(smem_raw, a, S);
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const ReplicaScalars rs = a.rs[r];
+    for (int k = tid; k < a.n_pad; k += ESB_THREADS) {
+        S.pos[k] = a.pos4[(size_t)r * a.n_pad + k];
+        const float4 v = a.vel4[(size_t)r * a.n_pad + k];
+        S.vx[k] = v.x; S.vy[k] = v.y; S.vz[k] = v.z;
+    }
+    for (int k = tid; k < a.n_tables * (int)(sizeof(DevTab) / 4); k += ESB_THREADS)
+        reinterpret_cast<int *>(S.tab)[k] = reinterpret_cast<const int *>(a.tabs)[k];
+    for (int k = tid; k < M_END; k += ESB_THREADS) S.misc[k] = 0;
+    __syncthreads();
+    load_setup(S, a, setup_id);
+    __syncthreads();
+    build_lists(S, a, r);
+    double en[3] = {0.0, 0.0, 0.0};
+    if (pair_mode == 1) force_phase<1, true>(S, a, r, soft_a, (float)rs.r0[1], (float)rs.r0[2], en);
+    else if (pair_mode == 2) force_phase<2, true>(S, a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], en);
+    __syncthreads();
+    double e_wall = 0.0;
+    int fail = 0;
+    for (int i = tid; i < a.n_atoms; i += ESB_THREADS) {
+        float fx = S.fx[i], fy = S.fy[i], fz = S.fz[i];
+        if (with_post)
+            fail |= post_force<true>(a, i, S.pos[i], S.vx[i], S.vy[i], S.vz[i], fx, fy, fz, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), eval, e_wall);
+        double *o = f_out + ((size_t)r * a.n_atoms + i) * 3;
+        o[0] = fx; o[1] = fy; o[2] = fz;
+    }
+    // block-reduce the four energies through shared memory (the force arrays are free now)
+    __syncthreads();
+    double *red = reinterpret_cast<double *>(S.fx);
+    const double mine[4] = {en[0], en[1], en[2], e_wall};
+    for (int q = 0; q < 4; q++) red[q * ESB_THREADS + tid] = mine[q];
+    __syncthreads();
+    if (tid < 4) {
+        double s = 0.0;
+        for (int k = 0; k < ESB_THREADS; k++) s += red[tid * ESB_THREADS + k];
+        e_out[(size_t)r * 4 + tid] = s;
+    }
+    if (tid == 0 && (fail | S.misc[M_FAIL])) atomicOr(&a.rs[r].status, fail | S.misc[M_FAIL]);
+}
+
+// double [R][N][3] (+types) <-> float4 state.  frozen beads carry bit 8 of the type word.
+extern "C" __global__ void esb_pack_kernel(const double *x, const double *v, const int *types, const unsigned char *frozen,
+                                           float4 *pos4, float4 *vel4, int n_atoms, int n_pad, int n_replicas, int replicate)
+{
+    const size_t total = (size_t)n_replicas * n_pad;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(q / n_pad), i = (int)(q % n_pad);
+        float4 p = make_float4(0.f, 0.f, 0.f, __int_as_float(0)), w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n_atoms) {
+            const size_t s = ((size_t)(replicate ? 0 : r) * n_atoms + i);
+            const int t = types[s] | (frozen[i] ? 0x100 : 0);
+            p = make_float4((float)x[3 * s], (float)x[3 * s + 1], (float)x[3 * s + 2], __int_as_float(t));
+            if (v) w = make_float4((float)v[3 * s], (float)v[3 * s + 1], (float)v[3 * s + 2], 0.f);
+        }
+        pos4[q] = p; vel4[q] = w;
+    }
+}
+
+extern "C" __global__ void esb_unpack_kernel(const float4 *pos4, const float4 *vel4, double *x, double *v, int *types,
+                                             int n_atoms, int n_pad, int n_replicas)
+{
+    const size_t total = (size_t)n_replicas * n_atoms;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(q / n_atoms), i = (int)(q % n_atoms);
+        const float4 p = pos4[(size_t)r * n_pad + i], w = vel4[(size_t)r * n_pad + i];
+        if (x) { x[3 * q] = p.x; x[3 * q + 1] = p.y; x[3 * q + 2] = p.z; }
+        if (v) { v[3 * q] = w.x; v[3 * q + 1] = w.y; v[3 * q + 2] = w.z; }
+        if (types) types[q] = __float_as_int(p.w) & 0xff;
+    }
+}
+
+size_t esb_smem_bytes(int n_pad, int n_tables) { return smem_bytes_for(n_pad, n_tables); }

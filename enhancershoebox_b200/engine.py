@@ -1,0 +1,357 @@
+"""ctypes binding of libesb.so + the batch engine the drivers use instead of the `lammps` module.
+
+`ShoeboxBatch` plays the role of the ``lammps()`` / ``IPyLammps`` pair in the reference drivers
+(``run_single_shoebox.py:323-325``) for a whole BATCH of replicas: it is configured with the same
+inputs (a ``make_input_file.py`` data file, the ``LJsoft_RSQ.table`` sections, the driver's
+``pair_coeff`` stream, box/promoter/threshold/activation parameters) and advances all replicas on
+one B200.  The library is required: if ``libesb.so`` is missing or no sm_100 GPU is present the
+constructor raises -- there is no CPU fallback and the oracle is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import ljsoft, protocol as P
+from .datafile import ShoeboxData
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libesb.so")
+MAXT = 12
+N_SHELL = 50
+FRAME_DOUBLES = 9
+MAP_IDS = {"A": 0, "B": 1, "T": 2}
+
+ST_WALL, ST_INNER, ST_NONFINITE, ST_NEIGH = 1, 2, 4, 8
+
+
+class EsbError(RuntimeError):
+    pass
+
+
+class ClosedForm(C.Structure):
+    _fields_ = [("valid", C.c_int), ("eps_eff", C.c_double), ("s", C.c_double), ("rc", C.c_double), ("c", C.c_double)]
+
+
+class ChunkDesc(C.Structure):
+    _fields_ = [("chunk_index", C.c_int), ("n_steps", C.c_int), ("pair_mode", C.c_int), ("map_id", C.c_int),
+                ("ramp_on", C.c_int), ("ramp_start", C.c_int64), ("ramp_stop", C.c_int64),
+                ("adapt_soft", C.c_int), ("adapt_bond1", C.c_int), ("adapt_bond2", C.c_int),
+                ("observe", C.c_int), ("expected_rnp", C.c_int)]
+
+
+_lib = None
+
+_SIGNATURES = {
+    "esb_last_error": (C.c_char_p, []),
+    "esb_version": (C.c_int, []),
+    "esb_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "esb_destroy": (C.c_int, [C.c_void_p]),
+    "esb_set_box": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "esb_set_topology": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
+    "esb_set_coeffs": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "esb_set_fixes": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]),
+    "esb_set_soft": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "esb_set_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ClosedForm)]),
+    "esb_table_from_section": (C.c_int, [C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
+                                         C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "esb_set_table_map": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "esb_set_layout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "esb_set_replica_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "esb_upload_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
+    "esb_download_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "esb_upload_state_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esb_download_state_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esb_n_pad": (C.c_int, [C.c_void_p]),
+    "esb_set_schedule": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ChunkDesc)]),
+    "esb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "esb_sync": (C.c_int, [C.c_void_p]),
+    "esb_forces": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "esb_get_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "esb_get_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "esb_get_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "esb_reset_counters": (C.c_int, [C.c_void_p]),
+    "esb_get_bond_r0": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "esb_get_step": (C.c_int64, [C.c_void_p]),
+    "esb_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "esb_aggregate_grouped": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                        C.POINTER(C.c_double), C.c_void_p]),
+}
+ABI_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load_library(path: str | None = None):
+    """dlopen libesb.so and attach the prototypes of include/esb.h.  Raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise EsbError(f"{p} not found: build it with `python -m enhancershoebox_b200.build` "
+                       "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(p)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def build_lookup(section, cut: float, tablength: int = P.TABLE_LENGTH):
+    """``pair_coeff I J file KEY cut`` -> (e, f, innersq, delta) via libesb's host builder."""
+    lib = load_library()
+    tlm1 = tablength - 1
+    e, f, prm = np.empty(tlm1), np.empty(tlm1), np.empty(3)
+    ef = np.ascontiguousarray(section.e, np.float64)
+    ff = np.ascontiguousarray(section.f, np.float64)
+    rc = lib.esb_table_from_section(int(section.n), float(section.rlo), float(section.rhi), _dp(ef), _dp(ff), float(cut),
+                                    int(tablength), _dp(e), _dp(f), _dp(prm))
+    if rc != 0:
+        raise EsbError(lib.esb_last_error().decode())
+    return e, f, float(prm[0]), float(prm[1])
+
+
+_table_cache: dict = {}
+
+
+def lookup_tables(tables: P.PairTables, table_file: str | None = None):
+    """LOOKUP arrays + closed forms for every (KEY, cut) of `tables` (cached per process)."""
+    key = (tuple(tables.specs), table_file)
+    if key in _table_cache:
+        return _table_cache[key]
+    keys = sorted({k for (k, _) in tables.specs})
+    if table_file is not None:
+        sections = ljsoft.read_table_file(table_file, set(keys))
+        missing = [k for k in keys if k not in sections]
+        if missing:
+            raise EsbError(f"{table_file}: sections not found: {missing}")
+    else:
+        sections = {k: ljsoft.generated_section(k) for k in keys}
+    lookup = [build_lookup(sections[k], c) for (k, c) in tables.specs]
+    cfs = []
+    for (k, _c) in tables.specs:
+        cf = ClosedForm()
+        if k in ljsoft.SECTION_INDEX and not ljsoft.SECTIONS[ljsoft.SECTION_INDEX[k]][5]:
+            g = ljsoft.section_geometry(k)
+            cf.valid, cf.eps_eff, cf.s, cf.rc, cf.c = 1, g.eps_eff, g.s, g.rc, g.c
+        cfs.append(cf)
+    _table_cache[key] = (lookup, cfs)
+    return lookup, cfs
+
+
+class ShoeboxBatch:
+    """A batch of independent shoebox replicas on one GPU."""
+
+    def __init__(self, data, n_replicas: int | None = None, driver: str = "genes_stages", condition: str = "Control",
+                 device: int = 0, table_file: str | None = None, seeds=None, thresholds=None, activations=None,
+                 langevin_mode: int = 1):
+        """`data`: one ShoeboxData (copied to all replicas) or a list with one per replica (same
+        topology).  `thresholds` = -x values, `activations` = -a values (per mille, as on the CLI)."""
+        self.lib = load_library()
+        datas = [data] if isinstance(data, ShoeboxData) else list(data)
+        d0 = datas[0]
+        self.R = int(n_replicas if n_replicas is not None else len(datas))
+        if len(datas) not in (1, self.R):
+            raise ValueError("data must hold one system or one per replica")
+        for d in datas[1:]:
+            if d.n_atoms != d0.n_atoms or not np.array_equal(d.bonds, d0.bonds) or not np.array_equal(d.angles, d0.angles):
+                raise ValueError("all replicas of a batch must share bead count and topology")
+        self.data0 = d0
+        self.N = d0.n_atoms
+        self.driver, self.condition = driver, condition
+        self.h = C.c_void_p()
+        self._check(self.lib.esb_create(device, self.R, self.N, d0.n_atom_types, C.byref(self.h)))
+        lo = np.ascontiguousarray(d0.box_lo, np.float64)
+        hi = np.ascontiguousarray(d0.box_hi, np.float64)
+        self._check(self.lib.esb_set_box(self.h, _dp(lo), _dp(hi)))
+        b = np.ascontiguousarray(d0.bonds, np.int32)
+        a = np.ascontiguousarray(d0.angles, np.int32)
+        fr = np.ascontiguousarray(d0.anchors(), np.int32)
+        self._check(self.lib.esb_set_topology(self.h, b.shape[0], _ip(b), a.shape[0], _ip(a), fr.shape[0], _ip(fr)))
+        bk = np.array([0.0, P.BOND_K, P.BOND_K])
+        br = np.array([0.0, P.BOND_R0[1], P.BOND_R0[2]])
+        ak = np.array([0.0, P.ANGLE_K[1], P.ANGLE_K[2]])
+        self._check(self.lib.esb_set_coeffs(self.h, _dp(bk), _dp(br), _dp(ak)))
+        self._check(self.lib.esb_set_fixes(self.h, P.DT, P.LANGEVIN_T, P.LANGEVIN_DAMP, langevin_mode, P.WALL_EPS, P.WALL_CUT))
+        sc = np.ascontiguousarray(P.soft_cutoffs(), np.float64)
+        self._check(self.lib.esb_set_soft(self.h, _dp(sc)))
+        # pair tables
+        phases = ("A", "B", "T") if condition in ("Hexanediol", "JQ-1") else ("A", "B")
+        self.tables = P.pair_tables(driver, condition, phases)
+        lookup, cfs = lookup_tables(self.tables, table_file)
+        nt = len(lookup)
+        f = np.ascontiguousarray(np.stack([l[1] for l in lookup]))
+        e = np.ascontiguousarray(np.stack([l[0] for l in lookup]))
+        inner = np.array([l[2] for l in lookup])
+        delta = np.array([l[3] for l in lookup])
+        cut = np.array([c for (_, c) in self.tables.specs], np.float64)
+        cf_arr = (ClosedForm * nt)(*cfs)
+        self._check(self.lib.esb_set_tables(self.h, nt, f.shape[1], _dp(f), _dp(e), _dp(inner), _dp(delta), _dp(cut), cf_arr))
+        for ph in phases:
+            m = np.ascontiguousarray(self.tables.maps[ph], np.int32).copy()
+            m[m < 0] = 0
+            self._check(self.lib.esb_set_table_map(self.h, MAP_IDS[ph], _ip(m)))
+        # layout for the fused measurements
+        enh = np.ascontiguousarray(d0.enhancer_atoms(), np.int32)
+        s5 = np.ascontiguousarray(d0.ser5p_atoms(), np.int32)
+        cr = np.ascontiguousarray(P.CLUSTER_R, np.float64)
+        self.gene_start, self.promoter_length = d0.gene_start(), d0.promoter_length()
+        self.n_rbprnp = int(d0.rbp_atoms().shape[0])
+        self._check(self.lib.esb_set_layout(self.h, self.gene_start, self.promoter_length, enh.shape[0], _ip(enh), s5.shape[0], _ip(s5), _dp(cr)))
+        self.set_replica_params(seeds, thresholds, activations)
+        # state
+        if len(datas) == 1:
+            self.upload_state(d0.x[None], d0.v[None], d0.types[None], replicate=True)
+        else:
+            self.upload_state(np.stack([d.x for d in datas]), np.stack([d.v for d in datas]), np.stack([d.types for d in datas]))
+        self.n_chunks = 0
+        self.plans = []
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EsbError(f"libesb error {rc}: {self.lib.esb_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.esb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def set_replica_params(self, seeds=None, thresholds=None, activations=None):
+        sd = None if seeds is None else np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, np.uint64), (self.R,)))
+        th = None if thresholds is None else np.ascontiguousarray(np.broadcast_to(np.asarray(thresholds, np.int32), (self.R,)))
+        pa = None if activations is None else np.ascontiguousarray(np.broadcast_to(np.asarray(activations, np.float64), (self.R,)) / 1000)
+        self._check(self.lib.esb_set_replica_params(
+            self.h,
+            None if sd is None else sd.ctypes.data_as(C.POINTER(C.c_uint64)),
+            None if th is None else _ip(th),
+            None if pa is None else _dp(pa)))
+
+    def upload_state(self, x, v, types, replicate: bool = False):
+        x = np.ascontiguousarray(x, np.float64)
+        t = np.ascontiguousarray(types, np.int32)
+        vv = None if v is None else np.ascontiguousarray(v, np.float64)
+        self._check(self.lib.esb_upload_state(self.h, _dp(x), None if vv is None else _dp(vv), _ip(t), int(replicate)))
+
+    def state(self):
+        """(x, v, types) of all replicas: the batch form of gather_atoms (run_single_shoebox.py:913-914)."""
+        x = np.empty((self.R, self.N, 3))
+        v = np.empty((self.R, self.N, 3))
+        t = np.empty((self.R, self.N), np.int32)
+        self._check(self.lib.esb_download_state(self.h, _dp(x), _dp(v), _ip(t)))
+        return x, v, t
+
+    def set_langevin(self, mode: int):
+        self._check(self.lib.esb_set_fixes(self.h, P.DT, P.LANGEVIN_T, P.LANGEVIN_DAMP, mode, P.WALL_EPS, P.WALL_CUT))
+
+    def set_schedule(self, n_chunks: int | None = None, observe: bool = True, plans=None, n_steps: int | None = None):
+        """Lay out the drivers' main loop (protocol.chunk_schedule) as the device programme."""
+        if plans is None:
+            plans = P.chunk_schedule(self.driver, self.condition, n_chunks)
+        t_rnp_final = 2000 if self.driver == "genes_stages" else P.N_RUNS + P.TREATMENT_DURATION.get(self.condition, 0)
+        slope = P.F_RNP_FINAL / (t_rnp_final - P.T_INDUCTION_ON)
+        c_rnp = -slope * P.T_INDUCTION_ON
+        descs = (ChunkDesc * len(plans))()
+        for k, pl in enumerate(plans):
+            d = descs[k]
+            d.chunk_index = pl.index
+            d.n_steps = pl.n_steps if n_steps is None else n_steps
+            d.pair_mode = 1 if pl.pair == "soft" else 2
+            d.map_id = 0 if pl.pair == "soft" else MAP_IDS[pl.pair]
+            d.ramp_on = int(pl.ramp is not None)
+            d.ramp_start, d.ramp_stop = pl.ramp if pl.ramp is not None else (0, 1)
+            d.adapt_soft, d.adapt_bond1, d.adapt_bond2 = int(pl.adapt_soft), int(pl.adapt_bond1), int(pl.adapt_bond2)
+            d.observe = int(observe)
+            i = pl.index
+            d.expected_rnp = int(((i + 1) * slope + c_rnp) * self.n_rbprnp) if (i + 1) >= P.T_INDUCTION_ON else -1
+        self._check(self.lib.esb_set_schedule(self.h, len(plans), descs))
+        self.n_chunks = len(plans)
+        self.plans = list(plans)
+
+    def run(self, chunk_begin: int = 0, n_chunks: int | None = None, stream=None, sync: bool = True):
+        """``L.run(tRun)`` for n_chunks Python timesteps, measurements and state machine fused."""
+        n = self.n_chunks - chunk_begin if n_chunks is None else n_chunks
+        self._check(self.lib.esb_run(self.h, chunk_begin, n, stream))
+        if sync:
+            self._check(self.lib.esb_sync(self.h))
+
+    def sync(self):
+        self._check(self.lib.esb_sync(self.h))
+
+    def forces(self, pair: str = "B", soft_a: float = 0.0, with_post: bool = False, eval_index: int = 0, use_arrays: bool = False):
+        """Parity hook: forces [R,N,3] and energies [R,4] (pair, bond, angle, wall) at the current state."""
+        f = np.empty((self.R, self.N, 3))
+        e = np.empty((self.R, 4))
+        mode = 0 if pair is None else (1 if pair == "soft" else 2)
+        mid = 0 if mode != 2 else MAP_IDS[pair]
+        self._check(self.lib.esb_forces(self.h, mode, mid, float(soft_a), int(with_post), int(eval_index), int(use_arrays), _dp(f), _dp(e)))
+        return f, e
+
+    def frames(self, chunk_begin: int = 0, n_chunks: int | None = None, with_hist: bool = False):
+        n = self.n_chunks - chunk_begin if n_chunks is None else n_chunks
+        out = np.empty((self.R, n, FRAME_DOUBLES))
+        hist = np.empty((self.R, n, N_SHELL - 1), np.int32) if with_hist else None
+        self._check(self.lib.esb_get_frames(self.h, chunk_begin, n, _dp(out), None if hist is None else _ip(hist)))
+        return (out, hist) if with_hist else out
+
+    def status(self):
+        st = np.empty(self.R, np.int32)
+        self._check(self.lib.esb_get_status(self.h, _ip(st)))
+        return st
+
+    def counters(self):
+        out = np.empty((self.R, 6), np.int64)
+        self._check(self.lib.esb_get_counters(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return dict(evals=out[:, 0], builds=out[:, 1], pairs=out[:, 2], listed=out[:, 3], steps=out[:, 4], total_active=out[:, 5])
+
+    def reset_counters(self):
+        self._check(self.lib.esb_reset_counters(self.h))
+
+    def bond_r0(self):
+        r0 = np.empty(3)
+        self._check(self.lib.esb_get_bond_r0(self.h, _dp(r0)))
+        return r0
+
+    @property
+    def step(self) -> int:
+        return int(self.lib.esb_get_step(self.h))
+
+    @property
+    def n_pad(self) -> int:
+        return int(self.lib.esb_n_pad(self.h))
+
+    def device_ptr(self, which: int) -> int:
+        return int(self.lib.esb_device_ptr(self.h, which) or 0)
+
+
+def aggregate_grouped(frames: np.ndarray, group: int = 5, contact_dist: float = 250.0, t_skip: int = 150, device: int = 0):
+    """dist_genestages_grouped.py rows (S5PInt, S2PInt, Contact, DistActivation) for frames
+    [n_runs, n_frames, 9]; groups of `group` consecutive runs (VGM/dist_genestages_grouped.py:70-106)."""
+    lib = load_library()
+    fr = np.ascontiguousarray(frames, np.float64)
+    n_runs, n_frames = fr.shape[0], fr.shape[1]
+    out = np.empty((n_runs // group, 4))
+    rc = lib.esb_aggregate_grouped(device, fr.ctypes.data_as(C.c_void_p), 0, n_runs, n_frames, group, contact_dist, t_skip, _dp(out), None)
+    if rc != 0:
+        raise EsbError(f"esb_aggregate_grouped failed with {rc}")
+    return out
