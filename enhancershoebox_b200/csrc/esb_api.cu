@@ -312,14 +312,14 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     const size_t tot = (size_t)n_replicas * h->n_pad;
     if ((rc = dev_alloc(&h->d_pos4, tot)) || (rc = dev_alloc(&h->d_vel4, tot)) || (rc = dev_alloc(&h->d_rs, (size_t)n_replicas)) ||
         (rc = dev_alloc(&h->d_frozen, (size_t)h->n_pad)) || (rc = dev_alloc(&h->d_nl_pool, (size_t)n_replicas * ESB_NL_POOL)) ||
-        (rc = dev_alloc(&h->d_nl_head, tot)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * 6))) {
+        (rc = dev_alloc(&h->d_nl_head, tot)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * ESB_N_COUNTERS))) {
         esb_destroy(h);
         return rc;
     }
     cudaMemset(h->d_pos4, 0, tot * sizeof(float4));
     cudaMemset(h->d_vel4, 0, tot * sizeof(float4));
     cudaMemset(h->d_frozen, 0, h->n_pad);
-    cudaMemset(h->d_counters, 0, (size_t)n_replicas * 6 * sizeof(unsigned long long));
+    cudaMemset(h->d_counters, 0, (size_t)n_replicas * ESB_N_COUNTERS * sizeof(unsigned long long));
     cudaMemset(h->d_nl_head, 0, tot * sizeof(unsigned int));
     if ((rc = push_rs(h))) { esb_destroy(h); return rc; }
     // empty topology by default
@@ -781,7 +781,7 @@ int esb_get_counters(esb_handle *h, int64_t *out)
 {
     if (!h || !out) return fail(ESB_EINVAL, "NULL argument");
     CK(cudaSetDevice(h->device));
-    CK(cudaMemcpy(out, h->d_counters, (size_t)h->R * 6 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, h->d_counters, (size_t)h->R * ESB_N_COUNTERS * sizeof(int64_t), cudaMemcpyDeviceToHost));
     return ESB_OK;
 }
 
@@ -789,7 +789,7 @@ int esb_reset_counters(esb_handle *h)
 {
     if (!h) return fail(ESB_EINVAL, "NULL handle");
     CK(cudaSetDevice(h->device));
-    CK(cudaMemset(h->d_counters, 0, (size_t)h->R * 6 * sizeof(int64_t)));
+    CK(cudaMemset(h->d_counters, 0, (size_t)h->R * ESB_N_COUNTERS * sizeof(int64_t)));
     return ESB_OK;
 }
 

@@ -17,6 +17,7 @@
 #define ESB_NL_CHUNK 2048            // arena chunk a lane-group grabs
 #define ESB_NL_MAXNB 1023            // neighbours per atom (12-bit count in the head word)
 #define ESB_NL_POOL (256 * 1024)     // u16 entries per replica arena
+#define ESB_N_COUNTERS 10             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases
 #define ESB_N_SETUPS 9               // 0 = pair soft, 1..4 = table maps 0..3 (closed form + patch), 5..8 = same maps, array lookups
 
 // One (KEY,cut) table.  plo..phi is the bin range served from the value array at poff (the
@@ -95,7 +96,7 @@ struct KArgs {
     double *frames;           // [R][max_chunks][9]
     unsigned short *hist;     // [R][max_chunks][49]
     int max_chunks;
-    unsigned long long *counters;  // [R][6]
+    unsigned long long *counters;  // [R][ESB_N_COUNTERS]
 };
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -617,6 +617,8 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
     for (int k = tid; k < M_END; k += ESB_THREADS) S.misc[k] = 0;
     const uint32_t k0 = (uint32_t)rs.seed, k1 = (uint32_t)(rs.seed >> 32);
     unsigned long long n_evals = 0, n_builds = 0, n_steps_done = 0, n_pairs = 0, n_listed = 0;
+    long long t_atom = 0, t_build = 0, t_force = 0, t_obs = 0, t_mark = clock64();
+#define ESB_TICK(acc) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; }
     int failed = 0;
 
     for (int c = chunk_begin; c < chunk_begin + n_chunks && !failed; c++) {
@@ -632,12 +634,15 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
         if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
         if (tid == 0) S.misc[M_WORK] = 0;
         __syncthreads();
+        ESB_TICK(t_obs)
         build_lists(S, a, r);
         n_builds++;
+        ESB_TICK(t_build)
         if (d.pair_mode == 1) force_phase<1, false>(S, a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
         else force_phase<2, false>(S, a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
         n_evals++;
         __syncthreads();
+        ESB_TICK(t_force)
         n_listed += (unsigned int)S.misc[M_CURLIST];
         for (int it = 0; it <= d.n_steps; it++) {
             const bool last_pass = (it == d.n_steps);
@@ -646,6 +651,7 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
             if (tid == 0) S.misc[M_WORK] = 0;
             flags |= S.misc[M_FAIL] << 1;
             flags = __syncthreads_or(flags);
+            ESB_TICK(t_atom)
             if (flags >> 1) { failed = flags >> 1; break; }
             if (last_pass) break;
             rs.step++;
@@ -655,11 +661,12 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
                 if (d.adapt_bond1) rs.r0[1] = ramp(a.ramp_bond[1][0], a.ramp_bond[1][1], rs.step, rb, re);
                 if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
             }
-            if (flags & 1) { build_lists(S, a, r); n_builds++; }
+            if (flags & 1) { build_lists(S, a, r); n_builds++; ESB_TICK(t_build) }
             if (d.pair_mode == 1) force_phase<1, false>(S, a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
             else force_phase<2, false>(S, a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
             n_evals++;
             __syncthreads();
+            ESB_TICK(t_force)
             n_listed += (unsigned int)S.misc[M_CURLIST];
         }
         n_pairs += (unsigned int)S.misc[M_PAIRS];
@@ -667,6 +674,7 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
         if (tid == 0) S.misc[M_PAIRS] = 0;
         if (failed) break;
         if (d.observe) observe(S, a, r, d, rs, delt, sig_nm);
+        ESB_TICK(t_obs)
     }
     __syncthreads();
     failed |= S.misc[M_FAIL];
@@ -677,7 +685,9 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
     if (tid == 0) {
         rs.status |= failed;
         a.rs[r] = rs;
-        unsigned long long *cn = a.counters + (size_t)r * 6;
+        unsigned long long *cn = a.counters + (size_t)r * ESB_N_COUNTERS;
+        cn[6] += (unsigned long long)t_atom; cn[7] += (unsigned long long)t_build;
+        cn[8] += (unsigned long long)t_force; cn[9] += (unsigned long long)t_obs;
         cn[0] += n_evals; cn[1] += n_builds;
         cn[2] += n_pairs;
         cn[3] += n_listed;

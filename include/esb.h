@@ -25,6 +25,7 @@ extern "C" {
 #define ESB_MAXT 12          /* atom types are 1..11 (run_single_shoebox.py:23-33); index 0 unused */
 #define ESB_MAX_TABLES 48
 #define ESB_N_SHELL 50       /* cluster_r = linspace(0.65, 2.5, 50) (run_single_shoebox.py:425)    */
+#define ESB_N_COUNTERS 10
 #define ESB_FRAME_DOUBLES 9  /* geneTrack.txt columns (run_single_shoebox.py:1496)                   */
 
 enum {
@@ -147,7 +148,9 @@ int esb_forces(esb_handle *h, int pair_mode, int map_id, double soft_a, int with
  * n_s5p_gene, state) (run_single_shoebox.py:1496); hist [R][n_chunks][49] ints or NULL (:1504-1519) */
 int esb_get_frames(esb_handle *h, int chunk_begin, int n_chunks, double *out, int *hist);
 int esb_get_status(esb_handle *h, int *status);                   /* [R] ESB_ST_* bits               */
-/* [R][6]: force evaluations, neighbour builds, in-cutoff pairs, listed pairs, steps, total_active_steps */
+/* [R][ESB_N_COUNTERS]: force evaluations, neighbour builds, in-cutoff (ordered) pairs, listed (ordered)
+ * pairs summed over evaluations, steps, total_active_steps, then SM cycles spent in the per-atom
+ * phase, list builds, force phase, set-up/observation */
 int esb_get_counters(esb_handle *h, int64_t *out);
 int esb_reset_counters(esb_handle *h);
 /* current bond r0 (after fix adapt) and MD step per handle */
