@@ -85,7 +85,7 @@ struct esb_handle {
     double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     bool have_box = false, have_topo = false, have_soft = false, have_tables = false, have_layout = false, have_state = false;
     bool setups_dirty = true;
-    double dt = 0.005, t_target = 1.0, t_damp = 0.5, wall_eps = 100.0, wall_cut = 3.0, skin = 0.3, cell_edge = 1.1;
+    double dt = 0.005, t_target = 1.0, t_damp = 0.5, wall_eps = 100.0, wall_cut = 3.0, skin = 0.3, cell_edge = 2.2;
     int langevin_mode = 1;
     double bond_k[3] = {0, 90.0, 90.0}, bond_r0[3] = {0, 1.0, 0.3}, angle_k[3] = {0, 100.0 / 60.0, 33.0};
     double soft_cut[ESB_MAXT * ESB_MAXT];
@@ -106,7 +106,7 @@ struct esb_handle {
     DevTab *d_tabs_closed = nullptr, *d_tabs_array = nullptr;
     float *d_tabval = nullptr, *d_tabe = nullptr;
     unsigned short *d_nl_pool = nullptr;
-    unsigned int *d_nl_head = nullptr;
+    uint2 *d_nl_qinfo = nullptr;
     esb_chunk_desc *d_descs = nullptr;
     int *d_enh = nullptr, *d_s5p = nullptr;
     double *d_cluster_r = nullptr;
@@ -153,7 +153,7 @@ int rebuild_setups(esb_handle *h)
         h->ncx = std::max(1, (int)ceil((h->hi[0] - h->lo[0]) / c));
         h->ncy = std::max(1, (int)ceil((h->hi[1] - h->lo[1]) / c));
         h->ncz = std::max(1, (int)ceil((h->hi[2] - h->lo[2]) / c));
-        if ((long long)h->ncx * h->ncy * h->ncz <= cap) break;
+        if ((long long)h->ncx * h->ncy * h->ncz * ESB_NCLASS <= cap) break;
         c *= 1.05;
     }
     const double cell = c;
@@ -166,24 +166,36 @@ int rebuild_setups(esb_handle *h)
         const HostTable &T = h->tables[t];
         DevTab d;
         memset(&d, 0, sizeof(d));
-        d.innersq = T.innersq; d.invdelta = 1.0 / T.delta; d.delta = (float)T.delta;
+        d.innersq = T.innersq; d.invdelta = 1.0 / T.delta; d.delta = (float)T.delta; d.invdelta_f = (float)(1.0 / T.delta);
         d.poff = t * h->tlm1; d.epoff = t * h->tlm1;
-        d.plo = 0; d.phi = h->tlm1;
+        d.plo = 0; d.phi = 0; d.p0hi = h->tlm1;
         d.cutsq = nextafterf((float)(T.cut * T.cut * (1.0 + 2e-7)), INFINITY);
         d.rcsq = 0.0f; d.K = 0.0f; d.is6 = 0.0f; d.c = 1.0f;
         arr[t] = d;
         eff_cut_arr[t] = T.cut;
         eff_cut_closed[t] = T.cut;
         if (T.cf.valid) {
-            // patch = bins where the spline-built LOOKUP value departs from the closed form at the midpoint
-            int plo = h->tlm1, phi = 0;
+            // patches = bins where the spline-built LOOKUP value departs from the closed form at the
+            // midpoint: a run at the start of the table and a run around rc
+            std::vector<char> bad(h->tlm1);
             for (int i = 0; i < h->tlm1; i++) {
                 const double mid = T.innersq + (i + 0.5) * T.delta;
                 const double fc = closed_f_over_r(T.cf, sqrt(mid));
-                if (fabs(T.f[i] - fc) > 1e-7 * (1.0 + fabs(T.f[i]))) { plo = std::min(plo, i); phi = std::max(phi, i + 1); }
+                bad[i] = fabs(T.f[i] - fc) > 1e-7 * (1.0 + fabs(T.f[i]));
             }
-            if (plo >= phi) { plo = 0; phi = 0; }
-            d.plo = plo; d.phi = phi;
+            const int irc = (int)std::min((double)h->tlm1 - 1, std::max(0.0, (T.cf.rc * T.cf.rc - T.innersq) / T.delta));
+            // low patch: from bin 0 up to the last bad bin that is followed by >= 2000 good bins before rc
+            int p0hi = 0, plo = h->tlm1, phi = 0;
+            {
+                int last_bad = -1;
+                const int stop = std::max(0, irc - 2000);
+                for (int i = 0; i < stop; i++) if (bad[i]) last_bad = i;
+                p0hi = last_bad + 1;
+                for (int i = stop; i < h->tlm1; i++) if (bad[i]) { plo = std::min(plo, i); phi = std::max(phi, i + 1); }
+                if (plo >= phi) { plo = 0; phi = 0; }
+                if (p0hi > h->tlm1 / 2) { p0hi = h->tlm1; plo = 0; phi = 0; }   // not a closed-form table after all
+            }
+            d.plo = plo; d.phi = phi; d.p0hi = p0hi;
             const double s6 = pow(T.cf.s, 6);
             d.K = (float)(24.0 * T.cf.eps_eff / s6);
             d.is6 = (float)(1.0 / s6);
@@ -191,6 +203,7 @@ int rebuild_setups(esb_handle *h)
             d.rcsq = (float)(T.cf.rc * T.cf.rc);
             double eff = std::max(T.cf.rc * T.cf.rc, T.innersq + phi * T.delta);
             eff = std::min(eff, T.cut * T.cut);
+            if (p0hi == h->tlm1) eff = T.cut * T.cut;
             d.cutsq = nextafterf((float)(eff * (1.0 + 2e-7)), INFINITY);
             eff_cut_closed[t] = sqrt(eff);
         }
@@ -261,7 +274,11 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     k.tabs = array_flavour ? h->d_tabs_array : h->d_tabs_closed;
     k.n_tables = (int)h->tables.size();
     k.tabval = h->d_tabval; k.tabe = h->d_tabe; k.tlm1 = h->tlm1;
-    k.nl_pool = h->d_nl_pool; k.nl_head = h->d_nl_head;
+    k.nl_pool = h->d_nl_pool; k.nl_qinfo = h->d_nl_qinfo;
+    {   // species classes (run_single_shoebox.py:23-33): chromatin-like {1,2,6,7,9,10,11}, actin 3, RBP 4, RNP 5, Ser5P 8
+        static const unsigned char cls[ESB_MAXT] = {0, 0, 0, 1, 2, 3, 0, 0, 4, 0, 0, 0};
+        memcpy(k.class_of, cls, ESB_MAXT);
+    }
     k.descs = h->d_descs;
     k.lay = h->lay; k.enh_idx = h->d_enh; k.s5p_idx = h->d_s5p; k.cluster_r = h->d_cluster_r;
     k.frames = h->d_frames; k.hist = h->d_hist; k.max_chunks = h->n_chunks;
@@ -312,7 +329,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     const size_t tot = (size_t)n_replicas * h->n_pad;
     if ((rc = dev_alloc(&h->d_pos4, tot)) || (rc = dev_alloc(&h->d_vel4, tot)) || (rc = dev_alloc(&h->d_rs, (size_t)n_replicas)) ||
         (rc = dev_alloc(&h->d_frozen, (size_t)h->n_pad)) || (rc = dev_alloc(&h->d_nl_pool, (size_t)n_replicas * ESB_NL_POOL)) ||
-        (rc = dev_alloc(&h->d_nl_head, tot)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * ESB_N_COUNTERS))) {
+        (rc = dev_alloc(&h->d_nl_qinfo, tot)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * ESB_N_COUNTERS))) {
         esb_destroy(h);
         return rc;
     }
@@ -320,7 +337,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     cudaMemset(h->d_vel4, 0, tot * sizeof(float4));
     cudaMemset(h->d_frozen, 0, h->n_pad);
     cudaMemset(h->d_counters, 0, (size_t)n_replicas * ESB_N_COUNTERS * sizeof(unsigned long long));
-    cudaMemset(h->d_nl_head, 0, tot * sizeof(unsigned int));
+    cudaMemset(h->d_nl_qinfo, 0, tot * sizeof(uint2));
     if ((rc = push_rs(h))) { esb_destroy(h); return rc; }
     // empty topology by default
     std::vector<uint2> bt((size_t)ESB_MAX_TERMS * 32, make_uint2(0, 0));
@@ -337,7 +354,7 @@ int esb_destroy(esb_handle *h)
     cudaSetDevice(h->device);
     cudaFree(h->d_pos4); cudaFree(h->d_vel4); cudaFree(h->d_rs); cudaFree(h->d_frozen); cudaFree(h->d_bterm);
     cudaFree(h->d_spec); cudaFree(h->d_setups); cudaFree(h->d_tabs_closed); cudaFree(h->d_tabs_array);
-    cudaFree(h->d_tabval); cudaFree(h->d_tabe); cudaFree(h->d_nl_pool); cudaFree(h->d_nl_head); cudaFree(h->d_descs);
+    cudaFree(h->d_tabval); cudaFree(h->d_tabe); cudaFree(h->d_nl_pool); cudaFree(h->d_nl_qinfo); cudaFree(h->d_descs);
     cudaFree(h->d_enh); cudaFree(h->d_s5p); cudaFree(h->d_cluster_r); cudaFree(h->d_frames); cudaFree(h->d_hist);
     cudaFree(h->d_counters);
     delete h;

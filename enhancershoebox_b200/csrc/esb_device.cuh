@@ -17,12 +17,14 @@
 #define ESB_NL_CHUNK 2048            // arena chunk a lane-group grabs
 #define ESB_NL_MAXNB 1023            // neighbours per atom (12-bit count in the head word)
 #define ESB_NL_POOL (256 * 1024)     // u16 entries per replica arena
+#define ESB_NCLASS 5                 // species classes for the slot sort: chromatin-like, actin, RBP, RNP, Ser5P
 #define ESB_N_COUNTERS 10             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases
 #define ESB_N_SETUPS 9               // 0 = pair soft, 1..4 = table maps 0..3 (closed form + patch), 5..8 = same maps, array lookups
 
-// One (KEY,cut) table.  plo..phi is the bin range served from the value array at poff (the
-// "patch"); outside it the closed form is evaluated at the bin midpoint.  Array-only tables are
-// expressed as plo = 0, phi = tlm1.
+// One (KEY,cut) table.  Bins [0,p0hi) and [plo,phi) are served from the value array at poff (the
+// "patches": the first bins, where the file's r grid is too coarse for the spline to follow the
+// closed form, and the bins around rc, where the spline rings across the force jump); everywhere
+// else the closed form is evaluated at the bin midpoint.  Array-only tables have p0hi = tlm1.
 struct DevTab {
     double innersq, invdelta;   // exact bin index: int((rsq - innersq) * invdelta)
     float cutsq;                // effective cutoff^2: beyond it every bin value is 0
@@ -31,8 +33,10 @@ struct DevTab {
     float is6;                  // 1 / s^6
     float c;                    // alpha (1-lam)^2
     float delta;
+    float invdelta_f;           // fp32 bin-index estimate (verified against the bin edges, see force_phase)
     int plo, phi, poff;
     int epoff;                  // offset of the full energy array (parity hook only)
+    int p0hi;
 };
 
 // Per pair-style set-up: everything indexed by ti*ESB_MAXT+tj.
@@ -87,7 +91,8 @@ struct KArgs {
     const float *tabe;        // energy arrays (hook)
     int tlm1;
     unsigned short *nl_pool;  // [R][ESB_NL_POOL]
-    unsigned int *nl_head;    // [R][n_pad]   start | count << 20
+    uint2 *nl_qinfo;          // [R][n_pad]   per bead in cell-sorted order: {list start, atom | count << 16}
+    unsigned char class_of[ESB_MAXT + 4];
     const esb_chunk_desc *descs;
     // observation
     Layout lay;

@@ -64,7 +64,7 @@ __device__ __forceinline__ void carve(unsigned char *base, const KArgs &a, Smem 
     S.dmisc = reinterpret_cast<double *>(base + o); o += (size_t)D_END * 8;
     S.misc = reinterpret_cast<int *>(base + o);
     S.cend = reinterpret_cast<unsigned short *>(S.fx);
-    S.sidx = S.cend + ((a.ncells + 2 + 7) & ~7);
+    S.sidx = S.cend + ((a.ncells * ESB_NCLASS + 2 + 7) & ~7);
 }
 
 __device__ __forceinline__ void load_setup(const Smem &S, const KArgs &a, int setup_id)
@@ -84,31 +84,43 @@ __device__ __forceinline__ int cell_coord(float x, float lo, float inv, int n)
 // Neighbour list build.  Stands in for LAMMPS' binned neighbour build (`neighbor 0.3 multi`,
 // `neigh_modify every 1 delay 10 check yes`, run_single_shoebox.py:532-533): per-type-pair
 // cutoff + skin, 1-2/1-3/1-4 partners excluded (default special_bonds).  Full list (both i->j and
-// j->i) so the force loop needs no scatter.  Deterministic: cells are sorted by atom index.
+// j->i) so the force loop needs no scatter.
+//
+// Beads are counting-sorted into slots = (cell, species class); inside a slot they are ordered by
+// atom index, so the result is deterministic.  The sorted order is also the processing order of
+// both the build and the force loop: four consecutive beads (a "quad": same cell, same class,
+// hence near-identical candidate ranges and list lengths) share a warp, one per group of ESB_G
+// lanes, and run in lock step.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int slot_of(const KArgs &a, const float4 p)
+{
+    const int cx = cell_coord(p.x, a.lo[0], a.cell_inv, a.ncx);
+    const int cy = cell_coord(p.y, a.lo[1], a.cell_inv, a.ncy);
+    const int cz = cell_coord(p.z, a.lo[2], a.cell_inv, a.ncz);
+    return ((cz * a.ncy + cy) * a.ncx + cx) * ESB_NCLASS + a.class_of[__float_as_int(p.w) & 0xff];
+}
+
 __device__ void build_lists(const Smem &S, const KArgs &a, int r)
 {
     const int tid = threadIdx.x, n = a.n_atoms;
     const int lane = tid & 31, warp = tid >> 5;
+    const int nslots = a.ncells * ESB_NCLASS;
     unsigned int *cw = reinterpret_cast<unsigned int *>(S.cend);
-    const int ncw = (a.ncells + 2 + 1) >> 1;
+    const int ncw = (nslots + 2 + 1) >> 1;
     for (int w = tid; w < ncw; w += ESB_THREADS) cw[w] = 0u;
-    if (tid == 0) { S.misc[M_WORK2] = 0; S.misc[M_POOLCUR] = 0; S.misc[M_CURLIST] = 0; }
+    if (tid == 0) { S.misc[M_POOLCUR] = 0; S.misc[M_CURLIST] = 0; }
     __syncthreads();
-    // count (cell c is stored at slot c+1 so that, after the scan, slot c holds start(c))
+    // count (slot s is stored at position s+1 so that, after the scan, position s holds start(s))
     for (int i = tid; i < n; i += ESB_THREADS) {
         const float4 p = S.pos[i];
         S.bx[i] = p.x; S.by[i] = p.y; S.bz[i] = p.z;
-        const int cx = cell_coord(p.x, a.lo[0], a.cell_inv, a.ncx);
-        const int cy = cell_coord(p.y, a.lo[1], a.cell_inv, a.ncy);
-        const int cz = cell_coord(p.z, a.lo[2], a.cell_inv, a.ncz);
-        const int slot = (cz * a.ncy + cy) * a.ncx + cx + 1;
+        const int slot = slot_of(a, p) + 1;
         atomicAdd(&cw[slot >> 1], 1u << (16 * (slot & 1)));
     }
     __syncthreads();
-    // inclusive scan over slots 0..ncells (slot 0 is 0): afterwards cend[c] = start of cell c
+    // inclusive scan over positions 0..nslots (position 0 is 0): afterwards cend[s] = start of slot s
     {
-        const int total = a.ncells + 1;
+        const int total = nslots + 1;
         const int per = (total + ESB_THREADS - 1) / ESB_THREADS;
         const int b0 = min(tid * per, total), b1 = min(b0 + per, total);
         int sum = 0;
@@ -126,19 +138,15 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
         for (int c = b0; c < b1; c++) { base += S.cend[c]; S.cend[c] = (unsigned short)base; }
     }
     __syncthreads();
-    // scatter: cend[c] (= start of c) is used as the cursor of cell c; afterwards cend[c] = end of c
+    // scatter: cend[s] (= start of s) is the cursor of slot s; afterwards cend[s] = end of s
     for (int i = tid; i < n; i += ESB_THREADS) {
-        const float4 p = S.pos[i];
-        const int cx = cell_coord(p.x, a.lo[0], a.cell_inv, a.ncx);
-        const int cy = cell_coord(p.y, a.lo[1], a.cell_inv, a.ncy);
-        const int cz = cell_coord(p.z, a.lo[2], a.cell_inv, a.ncz);
-        const int slot = (cz * a.ncy + cy) * a.ncx + cx;
+        const int slot = slot_of(a, S.pos[i]);
         const unsigned int old = atomicAdd(&cw[slot >> 1], 1u << (16 * (slot & 1)));
         S.sidx[(old >> (16 * (slot & 1))) & 0xffffu] = (unsigned short)i;
     }
     __syncthreads();
-    // order every cell by atom index (insertion sort; cells hold a handful of beads)
-    for (int c = tid; c < a.ncells; c += ESB_THREADS) {
+    // order every slot by atom index (insertion sort; slots hold a handful of beads)
+    for (int c = tid; c < nslots; c += ESB_THREADS) {
         const int s0 = c ? S.cend[c - 1] : 0, s1 = S.cend[c];
         for (int p = s0 + 1; p < s1; p++) {
             const unsigned short v = S.sidx[p];
@@ -149,28 +157,27 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
     }
     __syncthreads();
 
-    const int gl = tid & (ESB_G - 1);
-    const int gshift = lane & ~(ESB_G - 1);
-    const unsigned int gmask = ((1u << ESB_G) - 1u) << gshift;
+    const unsigned int FULL = 0xffffffffu;
+    const int gl = lane & (ESB_G - 1), grp = lane / ESB_G;
+    const int gshift = grp * ESB_G;
     unsigned short *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
-    unsigned int *head = a.nl_head + (size_t)r * a.n_pad;
+    uint2 *qinfo = a.nl_qinfo + (size_t)r * a.n_pad;
     int cursor = 0, limit = 0;
     unsigned int listed = 0;
-    for (;;) {
-        int idx = 0;
-        if (gl == 0) idx = atomicAdd(&S.misc[M_WORK2], 1);
-        idx = __shfl_sync(gmask, idx, gshift);
-        if (idx >= n) break;
-        const int i = n - 1 - idx;
-        if (limit - cursor < ESB_NL_MAXNB + 1) {
-            int c = 0;
-            if (gl == 0) c = atomicAdd(&S.misc[M_POOLCUR], ESB_NL_CHUNK);
-            c = __shfl_sync(gmask, c, gshift);
+    const int nquads = (n + 3) >> 2;
+    for (int q = warp; q < nquads; q += ESB_THREADS / 32) {
+        const int idx = 4 * q + grp;
+        bool valid = idx < n;
+        const int i = valid ? S.sidx[idx] : 0;
+        const bool need = valid && (limit - cursor < ESB_NL_MAXNB + 1);
+        int c = 0;
+        if (need && gl == 0) c = atomicAdd(&S.misc[M_POOLCUR], ESB_NL_CHUNK);
+        c = __shfl_sync(FULL, c, gshift);
+        if (need) {
             if (c + ESB_NL_CHUNK > ESB_NL_POOL) {
-                if (gl == 0) { atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH); head[i] = 0u; }
-                continue;
-            }
-            cursor = c; limit = c + ESB_NL_CHUNK;
+                if (gl == 0) atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH);
+                valid = false;
+            } else { cursor = c; limit = c + ESB_NL_CHUNK; }
         }
         const float4 pi = S.pos[i];
         const int ti = __float_as_int(pi.w) & 0xff;
@@ -181,46 +188,55 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
         const int x0 = max(cx - rng, 0), x1 = min(cx + rng, a.ncx - 1);
         const int y0 = max(cy - rng, 0), y1 = min(cy + rng, a.ncy - 1);
         const int z0 = max(cz - rng, 0), z1 = min(cz + rng, a.ncz - 1);
+        const int nrows = valid ? (y1 - y0 + 1) * (z1 - z0 + 1) : 0;
+        const int rows_max = __reduce_max_sync(FULL, nrows);
         const bool topo_i = i < a.n_topo;
         uint4 sp = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         if (topo_i) sp = *reinterpret_cast<const uint4 *>(a.spec + (size_t)i * ESB_MAX_SPEC);
         const float *cs = S.setup->cutsq_skin + ti * ESB_MAXT;
         int cnt = 0;
-        for (int z = z0; z <= z1; z++)
-            for (int y = y0; y <= y1; y++) {
-                const int row = (z * a.ncy + y) * a.ncx;
-                const int ka = (row + x0) ? S.cend[row + x0 - 1] : 0;
-                const int kb = S.cend[row + x1];
-                for (int k0 = ka; k0 < kb; k0 += ESB_G) {
-                    const int k = k0 + gl;
-                    bool ok = false;
-                    int j = 0;
-                    if (k < kb) {
-                        j = S.sidx[k];
-                        const float4 pj = S.pos[j];
-                        const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                        const float r2 = dx * dx + dy * dy + dz * dz;
-                        const int tj = __float_as_int(pj.w) & 0xff;
-                        ok = (r2 < cs[tj]) && (j != i);
-                        if (ok && topo_i && j < a.n_topo) {
-                            const unsigned int jj = (unsigned int)j;
-                            ok = !((sp.x & 0xffffu) == jj || (sp.x >> 16) == jj || (sp.y & 0xffffu) == jj || (sp.y >> 16) == jj ||
-                                   (sp.z & 0xffffu) == jj || (sp.z >> 16) == jj || (sp.w & 0xffffu) == jj || (sp.w >> 16) == jj);
-                        }
-                    }
-                    const unsigned int bits = (__ballot_sync(gmask, ok) >> gshift) & ((1u << ESB_G) - 1u);
-                    if (ok) {
-                        const int slot = cnt + __popc(bits & ((1u << gl) - 1u));
-                        if (slot < ESB_NL_MAXNB) pool[cursor + slot] = (unsigned short)j;
-                    }
-                    cnt += __popc(bits);
-                }
+        int yy = y0, zz = z0;
+        for (int row_i = 0; row_i < rows_max; row_i++) {
+            int ka = 0, kb = 0;
+            if (row_i < nrows) {
+                const int row = (zz * a.ncy + yy) * a.ncx;
+                const int s_first = (row + x0) * ESB_NCLASS;
+                ka = s_first ? S.cend[s_first - 1] : 0;
+                kb = S.cend[(row + x1) * ESB_NCLASS + ESB_NCLASS - 1];
+                if (++yy > y1) { yy = y0; zz++; }
             }
+            const int len_max = __reduce_max_sync(FULL, kb - ka);
+            for (int k0 = 0; k0 < len_max; k0 += ESB_G) {
+                const int k = ka + k0 + gl;
+                bool ok = false;
+                int j = 0;
+                if (k < kb) {
+                    j = S.sidx[k];
+                    const float4 pj = S.pos[j];
+                    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                    const float r2 = dx * dx + dy * dy + dz * dz;
+                    const int tj = __float_as_int(pj.w) & 0xff;
+                    ok = (r2 < cs[tj]) && (j != i);
+                    if (ok && topo_i && j < a.n_topo) {
+                        const unsigned int jj = (unsigned int)j;
+                        ok = !((sp.x & 0xffffu) == jj || (sp.x >> 16) == jj || (sp.y & 0xffffu) == jj || (sp.y >> 16) == jj ||
+                               (sp.z & 0xffffu) == jj || (sp.z >> 16) == jj || (sp.w & 0xffffu) == jj || (sp.w >> 16) == jj);
+                    }
+                }
+                const unsigned int bits = (__ballot_sync(FULL, ok) >> gshift) & ((1u << ESB_G) - 1u);
+                if (ok) {
+                    const int slot = cnt + __popc(bits & ((1u << gl) - 1u));
+                    if (slot < ESB_NL_MAXNB) pool[cursor + slot] = (unsigned short)j;
+                }
+                cnt += __popc(bits);
+            }
+        }
         if (cnt > ESB_NL_MAXNB) {
             if (gl == 0) atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH);
             cnt = ESB_NL_MAXNB;
         }
-        if (gl == 0) { head[i] = (unsigned int)cursor | ((unsigned int)cnt << 20); listed += cnt; }
+        if (!valid) cnt = 0;
+        if (idx < a.n_pad && gl == 0) { qinfo[idx] = make_uint2((unsigned int)cursor, (unsigned int)i | ((unsigned int)cnt << 16)); listed += cnt; }
         cursor += cnt;
     }
     if (listed) atomicAdd(&S.misc[M_CURLIST], (int)listed);
@@ -292,80 +308,101 @@ template <int MODE, bool ENERGY>
 __device__ void force_phase(const Smem &S, const KArgs &a, int r, const float soft_a, const float r0_1, const float r0_2,
                             double *energy /* [3] pair, bond, angle: per-thread partials (ENERGY only) */)
 {
+    const unsigned int FULL = 0xffffffffu;
     const int tid = threadIdx.x, n = a.n_atoms;
     const int lane = tid & 31;
-    const int gl = tid & (ESB_G - 1);
-    const int gshift = lane & ~(ESB_G - 1);
-    const unsigned int gmask = ((1u << ESB_G) - 1u) << gshift;
+    const int gl = lane & (ESB_G - 1), grp = lane / ESB_G;
     const unsigned short *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
-    const unsigned int *head = a.nl_head + (size_t)r * a.n_pad;
+    const uint2 *qinfo = a.nl_qinfo + (size_t)r * a.n_pad;
     unsigned int npairs = 0;
     double e_pair = 0.0, e_bond = 0.0, e_angle = 0.0;
-    for (;;) {
-        int idx = 0;
-        if (gl == 0) idx = atomicAdd(&S.misc[M_WORK], 1);
-        idx = __shfl_sync(gmask, idx, gshift);
-        if (idx >= n) break;
-        const int i = n - 1 - idx;
+    // quads of the cell-sorted order, dealt round-robin to the warps; the next quad's descriptor is
+    // fetched (L2) while the current one is processed
+    const int nquads = (n + 3) >> 2;
+    const int warp = tid >> 5;
+    uint2 qi_next = make_uint2(0u, 0u);
+    if (warp < nquads && 4 * warp + grp < n) qi_next = qinfo[4 * warp + grp];
+    for (int q = warp; q < nquads; q += ESB_THREADS / 32) {
+        const uint2 qi = qi_next;
+        const int qn = q + ESB_THREADS / 32;
+        qi_next = make_uint2(0u, 0u);
+        if (qn < nquads && 4 * qn + grp < n) qi_next = qinfo[4 * qn + grp];
+        const bool valid = 4 * q + grp < n;
+        const int i = (int)(qi.y & 0xffffu);
+        const int cnt = valid ? (int)(qi.y >> 16) : 0;
+        const unsigned short *nl = pool + qi.x;
         const float4 pi = S.pos[i];
         const int ti = __float_as_int(pi.w) & 0xff;
-        const unsigned int h = head[i];
-        const unsigned short *nl = pool + (h & 0xfffffu);
-        const int cnt = (int)(h >> 20);
+        const int cnt_max = __reduce_max_sync(FULL, cnt);
         const float *cutsq = S.setup->cutsq + ti * ESB_MAXT;
         const unsigned char *tabid = S.setup->tabid + ti * ESB_MAXT;
-        const double xid = (double)pi.x, yid = (double)pi.y, zid = (double)pi.z;
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-        for (int e = gl; e < cnt; e += ESB_G) {
-            const int j = nl[e];
-            const float4 pj = S.pos[j];
-            const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-            const float r2 = dx * dx + dy * dy + dz * dz;
-            const int tj = __float_as_int(pj.w) & 0xff;
-            if (r2 < cutsq[tj]) {
-                float fpair;
-                if (MODE == 1) {
-                    const float rc = sqrtf(cutsq[tj]);
-                    const float rr = sqrtf(r2);
-                    const float arg = 3.14159265358979323846f * rr / rc;
-                    fpair = (rr > 0.0f) ? soft_a * sinf(arg) * 3.14159265358979323846f / rc / rr : 0.0f;
-                    if (ENERGY) e_pair += 0.5 * (double)(soft_a * (1.0f + cosf(arg)));
-                } else {
-                    const DevTab &T = S.tab[tabid[tj]];
-                    const double ddx = __dsub_rn(xid, (double)pj.x), ddy = __dsub_rn(yid, (double)pj.y), ddz = __dsub_rn(zid, (double)pj.z);
-                    const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
-                    if (rsq < T.innersq) { atomicOr(&S.misc[M_FAIL], ESB_ST_INNER); continue; }
-                    const int it = (int)__dmul_rn(__dsub_rn(rsq, T.innersq), T.invdelta);
-                    if (it >= T.plo && it < T.phi) {
-                        fpair = a.tabval[T.poff + it];
+        int j_next = (gl < cnt) ? nl[gl] : 0;
+        for (int e0 = 0; e0 < cnt_max; e0 += ESB_G) {
+            const int e = e0 + gl;
+            const int j = j_next;
+            j_next = (e + ESB_G < cnt) ? nl[e + ESB_G] : 0;   // prefetch: the list lives in L2
+            if (e < cnt) {
+                const float4 pj = S.pos[j];
+                const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                const int tj = __float_as_int(pj.w) & 0xff;
+                if (r2 < cutsq[tj]) {
+                    float fpair;
+                    if (MODE == 1) {
+                        const float rc = sqrtf(cutsq[tj]);
+                        const float rr = sqrtf(r2);
+                        const float arg = 3.14159265358979323846f * rr / rc;
+                        fpair = (rr > 0.0f) ? soft_a * sinf(arg) * 3.14159265358979323846f / rc / rr : 0.0f;
+                        if (ENERGY) e_pair += 0.5 * (double)(soft_a * (1.0f + cosf(arg)));
                     } else {
-                        const float q = (float)T.innersq + ((float)it + 0.5f) * T.delta;
-                        if (q < T.rcsq) {
-                            const float q2 = q * q;
-                            const float x = fmaf(q2 * q, T.is6, T.c);
-                            const float inv = __frcp_rn(x);
-                            fpair = T.K * q2 * (2.0f - x) * (inv * inv * inv);
-                        } else {
-                            fpair = 0.0f;
+                        const DevTab &T = S.tab[tabid[tj]];
+                        // bin index: fp32 estimate, accepted when it is provably on the same side of
+                        // every bin edge as the exact value; otherwise recomputed in fp64 (unfused,
+                        // same operations as the oracle).
+                        const float u = (r2 - (float)T.innersq) * T.invdelta_f;
+                        int it = (int)u;
+                        const float frac = u - (float)it;
+                        const float margin = fmaf(u, 1.0e-6f, 1.0e-3f);
+                        if (!(frac > margin && frac < 1.0f - margin)) {
+                            const double ddx = __dsub_rn((double)pi.x, (double)pj.x), ddy = __dsub_rn((double)pi.y, (double)pj.y),
+                                         ddz = __dsub_rn((double)pi.z, (double)pj.z);
+                            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
+                            if (rsq < T.innersq) { atomicOr(&S.misc[M_FAIL], ESB_ST_INNER); continue; }
+                            it = (int)__dmul_rn(__dsub_rn(rsq, T.innersq), T.invdelta);
                         }
+                        if (it < T.p0hi || (it >= T.plo && it < T.phi)) {
+                            fpair = a.tabval[T.poff + it];
+                        } else {
+                            const float q = (float)T.innersq + ((float)it + 0.5f) * T.delta;
+                            if (q < T.rcsq) {
+                                const float q2 = q * q;
+                                const float x = fmaf(q2 * q, T.is6, T.c);
+                                float inv = __fdividef(1.0f, x);
+                                inv = inv * fmaf(-x, inv, 2.0f);
+                                fpair = T.K * q2 * (2.0f - x) * (inv * inv * inv);
+                            } else {
+                                fpair = 0.0f;
+                            }
+                        }
+                        if (ENERGY) e_pair += 0.5 * (double)a.tabe[T.epoff + min(it, a.tlm1 - 1)];
                     }
-                    if (ENERGY) e_pair += 0.5 * (double)a.tabe[T.epoff + min(it, a.tlm1 - 1)];
+                    fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+                    npairs++;
                 }
-                fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
-                npairs++;
             }
         }
-        if (i < a.n_topo) {
+        if (valid && i < a.n_topo) {
             const uint2 term = a.bterm[(size_t)gl * a.n_topo_pad + i];
             bonded_term<ENERGY>(S, a, pi, term, r0_1, r0_2, fx, fy, fz, e_bond, e_angle);
         }
 #pragma unroll
         for (int d = ESB_G >> 1; d >= 1; d >>= 1) {
-            fx += __shfl_xor_sync(gmask, fx, d);
-            fy += __shfl_xor_sync(gmask, fy, d);
-            fz += __shfl_xor_sync(gmask, fz, d);
+            fx += __shfl_xor_sync(FULL, fx, d);
+            fy += __shfl_xor_sync(FULL, fy, d);
+            fz += __shfl_xor_sync(FULL, fz, d);
         }
-        if (gl == 0) { S.fx[i] = fx; S.fy[i] = fy; S.fz[i] = fz; }
+        if (valid && gl == 0) { S.fx[i] = fx; S.fy[i] = fy; S.fz[i] = fz; }
     }
     if (npairs) atomicAdd(&S.misc[M_PAIRS], (int)npairs);
     if (ENERGY) { energy[0] += e_pair; energy[1] += e_bond; energy[2] += e_angle; }
