@@ -504,7 +504,7 @@ __device__ __forceinline__ double dist_sq3(const double ax, const double ay, con
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-__device__ void observe(const Smem &S, const KArgs &a, int r, const esb_chunk_desc &d, ReplicaScalars &rs, double delt, double sig_nm)
+__device__ void observe(const Smem &S, const KArgs &a, int r, const esb_chunk_desc &d, ReplicaScalars &rs, double delt, double sig_nm, int slot)
 {
     const int tid = threadIdx.x;
     const Layout L = a.lay;
@@ -612,8 +612,8 @@ __device__ void observe(const Smem &S, const KArgs &a, int r, const esb_chunk_de
             }
         }
         // --- geneTrack record (:1496) ---
-        if (i < a.max_chunks) {
-            double *f = a.frames + ((size_t)r * a.max_chunks + i) * ESB_FRAME_DOUBLES;
+        if (slot < a.max_chunks) {
+            double *f = a.frames + ((size_t)r * a.max_chunks + slot) * ESB_FRAME_DOUBLES;
             f[0] = __dmul_rn((double)(i + 1), delt);
             f[1] = __dmul_rn(S.dmisc[D_PROBE], sig_nm);
             f[2] = __dmul_rn(S.dmisc[D_PROBE + 1], sig_nm);
@@ -625,9 +625,9 @@ __device__ void observe(const Smem &S, const KArgs &a, int r, const esb_chunk_de
             f[8] = (double)rs.gene_state;
         }
     }
-    if (d.chunk_index < a.max_chunks && a.hist)
+    if (slot < a.max_chunks && a.hist)
         for (int k = tid; k < ESB_N_SHELL - 1; k += ESB_THREADS)
-            a.hist[((size_t)r * a.max_chunks + d.chunk_index) * (ESB_N_SHELL - 1) + k] = (unsigned short)S.misc[M_HIST + k];
+            a.hist[((size_t)r * a.max_chunks + slot) * (ESB_N_SHELL - 1) + k] = (unsigned short)S.misc[M_HIST + k];
     __syncthreads();
 }
 
@@ -710,7 +710,7 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
         __syncthreads();
         if (tid == 0) S.misc[M_PAIRS] = 0;
         if (failed) break;
-        if (d.observe) observe(S, a, r, d, rs, delt, sig_nm);
+        if (d.observe) observe(S, a, r, d, rs, delt, sig_nm, c);
         ESB_TICK(t_obs)
     }
     __syncthreads();

@@ -1,0 +1,58 @@
+"""(e) sharding + end-of-run gather; world_size 2 over gloo on CPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from enhancershoebox_b200 import sweep
+
+
+def test_shard_ranges_cover_everything():
+    for n, w in ((4096, 8), (2304, 8), (64, 1), (10, 4), (3, 8)):
+        spans = [sweep.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        c = sweep.shard_counts(n, w)
+        assert sum(c) == n and max(c) - min(c) <= 1
+    assert sweep.shard_counts(4096, 8) == [512] * 8
+    with pytest.raises(ValueError):
+        sweep.shard_range(10, 4, 4)
+
+
+def test_sweep_grid_matches_launcher():
+    g = sweep.sweep_conditions()
+    assert len(g) == 3 * 10 * 11 * 100 == 33000        # rows of summary_contact_all_Thresholds10-100.txt
+    assert g[0] == (1, 10, 1, 1) and g[-1] == (3, 100, 100, 100)
+
+
+def _worker(rank, world, port, n_total, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = sweep.shard_range(n_total, rank, world)
+    local = np.arange(lo, hi, dtype=np.float64)[:, None] * np.array([1.0, 10.0, 100.0, np.nan])[None, :]
+    full = sweep.gather_rows(local, n_total)
+    q.put((rank, full))
+    dist.destroy_process_group()
+
+
+def test_gather_rows_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    q = ctx.Queue()
+    n_total = 7                                           # uneven shards: 4 + 3
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    exp = np.arange(n_total, dtype=np.float64)[:, None] * np.array([1.0, 10.0, 100.0, np.nan])[None, :]
+    for r in range(2):
+        assert np.array_equal(got[r], exp, equal_nan=True)
