@@ -457,7 +457,8 @@ __device__ __forceinline__ int post_force(const KArgs &a, int i, const float4 p,
 // [LAMMPS-ext] FixNVE: final_integrate of step n (v += dt/2 f) and initial_integrate of step n+1
 // (v += dt/2 f; x += dt v) are adjacent per-atom operations and are fused here
 // (fix 1 all nve, timestep 0.005: run_single_shoebox.py:643, 680).
-// Returns (rebuild needed) | (failure bits << 1).
+// Returns non-zero when this thread saw a bead move further than skin/2 since the last build;
+// failures (wall crossing, non-finite values) are OR-ed into S.misc[M_FAIL].
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int atom_phase(const Smem &S, const KArgs &a, const bool do_final, const bool do_initial,
                                           const uint32_t k0, const uint32_t k1, const unsigned long long eval)
@@ -470,7 +471,7 @@ __device__ __forceinline__ int atom_phase(const Smem &S, const KArgs &a, const b
         float vx = S.vx[i], vy = S.vy[i], vz = S.vz[i];
         float fx = S.fx[i], fy = S.fy[i], fz = S.fz[i];
         const int fail = post_force<false>(a, i, p, vx, vy, vz, fx, fy, fz, k0, k1, eval, dummy);
-        flags |= fail << 1;
+        if (fail) atomicOr(&S.misc[M_FAIL], fail);
         if (do_final) { vx += dtf * fx; vy += dtf * fy; vz += dtf * fz; }
         if (do_initial) {
             vx += dtf * fx; vy += dtf * fy; vz += dtf * fz;
@@ -669,7 +670,6 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
         if (d.adapt_soft) rs.soft_a = ramp(a.ramp_soft[0], a.ramp_soft[1], rs.step, rb, re);
         if (d.adapt_bond1) rs.r0[1] = ramp(a.ramp_bond[1][0], a.ramp_bond[1][1], rs.step, rb, re);
         if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
-        if (tid == 0) S.misc[M_WORK] = 0;
         __syncthreads();
         ESB_TICK(t_obs)
         build_lists(S, a, r);
@@ -683,13 +683,13 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
         n_listed += (unsigned int)S.misc[M_CURLIST];
         for (int it = 0; it <= d.n_steps; it++) {
             const bool last_pass = (it == d.n_steps);
-            int flags = atom_phase(S, a, it > 0, !last_pass, k0, k1, rs.eval);
+            // __syncthreads_or only tells whether ANY thread passed non-zero, so it carries the
+            // rebuild vote; the failure bits travel through shared memory
+            const int rebuild = __syncthreads_or(atom_phase(S, a, it > 0, !last_pass, k0, k1, rs.eval));
             rs.eval++;
-            if (tid == 0) S.misc[M_WORK] = 0;
-            flags |= S.misc[M_FAIL] << 1;
-            flags = __syncthreads_or(flags);
             ESB_TICK(t_atom)
-            if (flags >> 1) { failed = flags >> 1; break; }
+            failed = S.misc[M_FAIL];
+            if (failed) break;
             if (last_pass) break;
             rs.step++;
             n_steps_done++;
@@ -698,7 +698,7 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
                 if (d.adapt_bond1) rs.r0[1] = ramp(a.ramp_bond[1][0], a.ramp_bond[1][1], rs.step, rb, re);
                 if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
             }
-            if (flags & 1) { build_lists(S, a, r); n_builds++; ESB_TICK(t_build) }
+            if (rebuild) { build_lists(S, a, r); n_builds++; ESB_TICK(t_build) }
             if (d.pair_mode == 1) force_phase<1, false>(S, a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
             else force_phase<2, false>(S, a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
             n_evals++;
@@ -765,6 +765,7 @@ esb_forces_kernel(const KArgs a, const int pair_mode, const int setup_id, const 
         float fx = S.fx[i], fy = S.fy[i], fz = S.fz[i];
         if (with_post)
             fail |= post_force<true>(a, i, S.pos[i], S.vx[i], S.vy[i], S.vz[i], fx, fy, fz, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), eval, e_wall);
+        if (fail) atomicOr(&S.misc[M_FAIL], fail);
         double *o = f_out + ((size_t)r * a.n_atoms + i) * 3;
         o[0] = fx; o[1] = fy; o[2] = fz;
     }
@@ -779,7 +780,7 @@ esb_forces_kernel(const KArgs a, const int pair_mode, const int setup_id, const 
         for (int k = 0; k < ESB_THREADS; k++) s += red[tid * ESB_THREADS + k];
         e_out[(size_t)r * 4 + tid] = s;
     }
-    if (tid == 0 && (fail | S.misc[M_FAIL])) atomicOr(&a.rs[r].status, fail | S.misc[M_FAIL]);
+    if (tid == 0 && S.misc[M_FAIL]) atomicOr(&a.rs[r].status, S.misc[M_FAIL]);
 }
 
 // double [R][N][3] (+types) <-> float4 state.  frozen beads carry bit 8 of the type word.

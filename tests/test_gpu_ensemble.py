@@ -1,0 +1,55 @@
+"""Level 3: ensemble statistics of the device path against the fp64 oracle (statistical parity).
+
+Reference ensemble: tests/golden/oracle_ensemble_box11.npz = 48 oracle replicas x 400 chunks
+(box 11, promoter 3, -x 20, -a 100; made by tests/golden/make_oracle_ensemble.py).  The device runs
+192 replicas of the same protocol with different seeds.  Window means must agree within 4.5
+standard errors of the difference (both ensembles contribute); quantities fixed by the protocol
+(RNP count, frame times) must agree exactly."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from enhancershoebox_b200 import datafile, engine as E
+
+pytestmark = pytest.mark.gpu
+WINDOWS = ((20, 100), (100, 200), (200, 300), (300, 400))
+
+
+def _sem_diff(a, b):
+    return np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+
+
+def test_ensemble_matches_oracle():
+    z = np.load(os.path.join(GOLDEN, "oracle_ensemble_box11.npz"))
+    nch, thr, act = [int(v) for v in z["meta"]]
+    R = 192
+    datas = [datafile.make_shoebox(11, 3, False, seed=10_000 + r) for r in range(R)]
+    eng = E.ShoeboxBatch(datas, seeds=np.arange(R) + 777, thresholds=thr, activations=act)
+    eng.set_schedule(nch, observe=True)
+    eng.run()
+    assert np.all(eng.status() == 0) and np.all(z["status"] == 0)
+    fr = eng.frames()
+    x, v, t = eng.state()
+    # exact, protocol-determined quantities
+    assert np.array_equal(fr[:, :, 0], np.tile((np.arange(nch) + 1) * 6.0, (R, 1)))
+    assert np.all((t == 5).sum(axis=1) == z["nrnp"][0, -1])
+    assert np.all(fr[:, :150, 8] == 0) and np.all(fr[:, 150, 8] >= 1)
+    # temperature: <KE>/N = 3/2 kT (N - 4 anchors)/N
+    ke = 0.5 * (v ** 2).sum(axis=(1, 2)) / x.shape[1]
+    assert abs(ke.mean() - z["ke"][:, 20:].mean()) < 0.02
+    report = []
+    for lo, hi in WINDOWS:
+        for name, col in (("d_rp", 4), ("d_rg", 5), ("n_prom", 6), ("n_gene", 7)):
+            g = fr[:, lo:hi, col].mean(axis=1)
+            o = z[name][:, lo:hi].astype(np.float64).mean(axis=1)
+            zscore = (g.mean() - o.mean()) / _sem_diff(g, o)
+            report.append((lo, hi, name, g.mean(), o.mean(), zscore))
+            assert abs(zscore) < 4.5, report[-1]
+        ga = (fr[:, lo:hi, 8] == 2).mean(axis=1)
+        oa = (z["state"][:, lo:hi] == 2).mean(axis=1)
+        if lo >= 100:
+            assert abs(ga.mean() - oa.mean()) < 4.5 * _sem_diff(ga, oa) + 1e-3, (lo, hi, ga.mean(), oa.mean())
+    print("\n".join(f"[{lo},{hi}) {n}: device {g:.2f} oracle {o:.2f} z {zs:+.2f}" for lo, hi, n, g, o, zs in report))
+    eng.close()

@@ -70,8 +70,9 @@ def test_bin_index_is_exact(eng, orc, snapshots):
     fo, _, _ = orc.forces()
     eng.upload_state(np.stack([x] * 3), np.stack([v] * 3), np.stack([t] * 3))
     fg, _ = eng.forces("B", use_arrays=True)
-    per_atom = np.abs(fg[0] - fo).max(axis=1) / (np.abs(fo).max(axis=1) + 1.0)
-    assert per_atom.max() < 2e-6
+    # one flipped bin on a strongly repulsive pair (F ~ 50, neighbouring bins differ by ~1e-4 relative)
+    # would show up as ~4e-5 of the largest force; fp32 accumulation alone stays below 1e-6
+    assert np.abs(fg[0] - fo).max() / np.abs(fo).max() < 1e-6
 
 
 def test_pairs_excluded_and_counted(eng, orc, snapshots, box11):
