@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the EnhancerShoeBox hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME]
+
+A "step" is one Python timestep of the reference drivers ("chunk"): `run 200` + the per-chunk
+measurements / gene state machine / RNP ramp, over a whole batch of replicas.  The metric is
+BASELINE.json's: aggregate replica-timesteps/s (bead-steps/s is reported next to it).
+
+Workloads (config.workload):
+  box12_p3_x512   box 12, promoter 3, 512 replicas per GPU  -- the per-GPU share of BASELINE.json
+                  configs[3] (4096-replica box-12 ensemble on 8 GPUs); weak scaling.  DEFAULT.
+  box11_p3_x444   box 11, promoter 3, 444 replicas per GPU
+All replicas start from an equilibrated mid-run frame (chunk 1000 of 2000, 41 % RNP; produced by the
+oracle, tests/golden/snap_box12_chunk1000.npz) with distinct Langevin seeds, so the pair counts are
+those of a production run, not of the dilute initial condition.
+
+--impl reference times the CPU restatement of the reference's LAMMPS path (oracle/, "port": LAMMPS
+itself is not installable here) on all host cores, on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+T_RUN = 200
+START_CHUNK = 1000
+
+WORKLOADS = {
+    "box12_p3_x512": dict(box=12, promoter=3, replicas=512, snapshot="snap_box12_chunk1000.npz", tag="1000"),
+    "box11_p3_x444": dict(box=11, promoter=3, replicas=444, snapshot="snap_box11.npz", tag="500"),
+}
+
+
+def load_snapshot(w):
+    from enhancershoebox_b200 import datafile
+    z = np.load(os.path.join(ROOT, "tests", "golden", w["snapshot"]))
+    d = datafile.make_shoebox(w["box"], w["promoter"], False, seed=7)
+    tag = w["tag"]
+    return d, z["x" + tag].astype(np.float64), z["v" + tag].astype(np.float64), z["t" + tag].astype(np.int32)
+
+
+def flops_per_replica_step(pairs_in_cut: float, n_atoms: int, n_bonds: int, n_angles: int) -> float:
+    """Algorithmic work: 34 flop per in-cutoff pair (each unordered pair once),
+    40 per bead-step, 25 per bond, 55 per angle.  Rejected candidates are not algorithmic work."""
+    return 34.0 * pairs_in_cut + 40.0 * n_atoms + 25.0 * n_bonds + 55.0 * n_angles
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def latest_traffic():
+    """dram bytes per launch of the step kernel from the committed ncu summary (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "latest.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference(w, seconds_budget: float, threads: int | None = None):
+    """The oracle (CPU restatement of the LAMMPS path) on `threads` host cores, one replica per
+    thread, on a bounded sample of the workload: every thread advances its replica chunk by chunk
+    from the same mid-run frame until the budget is spent."""
+    from concurrent.futures import ThreadPoolExecutor
+    from enhancershoebox_b200 import ljsoft, protocol as P
+    from oracle import esb_oracle as O
+    O.build_native()
+    d, x, v, t = load_snapshot(w)
+    pt = P.pair_tables("genes_stages")
+    secs = {k: ljsoft.generated_section(k) for k in sorted({s[0] for s in pt.specs})}
+    lookup = [O.build_lookup_table(secs[k], c) for (k, c) in pt.specs]
+    threads = threads or (os.cpu_count() or 1)
+    plan = P.chunk_schedule("genes_stages", n_chunks=START_CHUNK + 1)[START_CHUNK]
+
+    def make(k):
+        o = O.Oracle(d, pt, lookup, seed=1 + k)
+        o.set_state(t, x, v)
+        return o
+
+    oracles = [make(k) for k in range(threads)]
+    deadline = [0.0]
+
+    def work(o):
+        n = 0
+        while True:
+            if o.run_chunk(plan) != 0:
+                raise RuntimeError("oracle replica failed")
+            n += 1
+            if time.perf_counter() >= deadline[0]:
+                return n
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda o: (o.apply_plan(plan), o.run(20)), oracles))          # warm-up (neighbour lists, caches)
+        t0 = time.perf_counter()
+        deadline[0] = t0 + seconds_budget
+        chunks = list(ex.map(work, oracles))
+        dt = time.perf_counter() - t0
+    steps = sum(chunks) * T_RUN
+    pairs = np.mean([o.counters()["pairs_in_cut"] / max(o.counters()["evals"], 1) for o in oracles])
+    return dict(value=steps / dt, unit="replica-steps/s", cores=threads, kind="port",
+                sample=f"{sum(chunks)} chunks x {T_RUN} steps on {threads} threads from the chunk-{START_CHUNK} frame in {dt:.1f} s",
+                pairs_in_cut=float(pairs), seconds=dt, bead_steps_per_s=steps / dt * d.n_atoms)
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    secs = min(60.0, max(5.0, 4.0 * args.steps))
+    cb = cpu_reference(w, secs)
+    d, *_ = load_snapshot(w)
+    line = {
+        "impl": "reference", "metric": "replica_timesteps_per_s", "value": cb["value"], "unit": "replica-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "n_atoms": d.n_atoms, "md_steps_per_step": T_RUN, "start_chunk": START_CHUNK,
+                   "note": "CPU restatement of the reference's LAMMPS command stream (LAMMPS itself is not installable here)"},
+        "bead_steps_per_s": cb["bead_steps_per_s"],
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "replica-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_native(args, w):
+    import torch
+    import torch.distributed as dist
+    from enhancershoebox_b200 import build as B, engine as E, protocol as P
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B.build()
+    d, x, v, t = load_snapshot(w)
+    R = args.replicas or w["replicas"]
+    K, W = args.steps, args.warmup
+    eng = E.ShoeboxBatch(d, n_replicas=R, seeds=np.arange(R, dtype=np.uint64) + 1 + 100003 * rank,
+                         thresholds=80, activations=30, device=local)
+    eng.upload_state(x[None], v[None], t[None], replicate=True)
+    plans = P.chunk_schedule("genes_stages", n_chunks=START_CHUNK + W + 2 * K + 2)[START_CHUNK:]
+    eng.set_schedule(plans=plans, observe=True)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    for c in range(W):
+        eng.run(c, 1, stream=sp, sync=False)
+    barrier()
+    eng.reset_counters()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for c in range(W, W + K):
+        eng.run(c, 1, stream=sp, sync=False)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    cnt = eng.counters()
+    status = eng.status()
+
+    # ---- end-to-end through the host-facing API: host state in, chunk, host state + records out ----
+    n_pad = eng.n_pad
+    h_pos = torch.empty((R, n_pad, 4), dtype=torch.float32).pin_memory()
+    h_vel = torch.empty((R, n_pad, 4), dtype=torch.float32).pin_memory()
+    lib = eng.lib
+    lib.esb_download_state_f32(eng.h, h_pos.data_ptr(), h_vel.data_ptr(), sp)
+    torch.cuda.synchronize()
+    h_frames = torch.empty((R, 9), dtype=torch.float64).pin_memory()
+
+    def e2e_step(c):
+        lib.esb_upload_state_f32(eng.h, h_pos.data_ptr(), h_vel.data_ptr(), sp)          # H2D: this step's input
+        eng.run(c, 1, stream=sp, sync=False)
+        lib.esb_download_state_f32(eng.h, h_pos.data_ptr(), h_vel.data_ptr(), sp)        # D2H: gather_atoms
+        lib.esb_get_frames_async(eng.h, c, 1, h_frames.data_ptr(), sp)                    # D2H: this chunk's geneTrack records
+        stream.synchronize()                                                              # the host consumes the result
+
+    for c in range(W + K, W + K + 1):
+        e2e_step(c)
+    barrier()
+    t0 = time.perf_counter()                      # end to end is what the host sees: wall clock around synchronous steps
+    for c in range(W + K + 1, W + 2 * K + 1):
+        e2e_step(c)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t_max = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    fails = torch.tensor([int((status != 0).sum())], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fails, op=dist.ReduceOp.SUM)
+    ms, ms_e2e = float(t_max[0]), float(t_max[1])
+
+    if rank == 0:
+        total_R = R * world
+        value = total_R * T_RUN * K / (ms * 1e-3)
+        e2e_value = total_R * T_RUN * K / (ms_e2e * 1e-3)
+        evals = float(cnt["evals"].sum())
+        pairs_in_cut = float(cnt["pairs"].sum()) / evals / 2.0
+        listed = float(cnt["listed"].sum()) / evals / 2.0
+        fl = flops_per_replica_step(pairs_in_cut, d.n_atoms, d.bonds.shape[0], d.angles.shape[0])
+        peaks, which = measured_peaks()
+        fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12     # TFLOP/s
+        launch_ms = ms / K
+        achieved = (R * T_RUN * fl) / (launch_ms * 1e-3) / 1e12                               # per GPU, per launch
+        prof = latest_traffic()
+        cyc = {k: float(cnt[k].sum()) for k in ("cyc_atom", "cyc_build", "cyc_force", "cyc_other")}
+        cyc_tot = sum(cyc.values()) or 1.0
+        line = {
+            "metric": "replica_timesteps_per_s", "value": value, "unit": "replica-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "replicas_per_gpu": R, "n_atoms": d.n_atoms, "md_steps_per_step": T_RUN,
+                       "start_chunk": START_CHUNK, "l2": "state is SMEM-resident; neighbour arenas (R x 512 KiB) exceed L2",
+                       "parallelism": f"replicas sharded over {world} GPU(s), no collective on the step path"},
+            "bead_steps_per_s": value * d.n_atoms,
+            "e2e": {"value": e2e_value, "unit": "replica-steps/s", "h2d_bytes_per_step": int(2 * R * n_pad * 16),
+                    "d2h_bytes_per_step": int(2 * R * n_pad * 16 + R * 72), "ms_per_step": ms_e2e / K},
+            "gpu_launches": K,
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                         "traffic": None if not prof else prof.get("dram_bytes_per_launch"),
+                         "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({which} MEASURED_PEAKS.json); MEASURED_PEAKS has no FP32 entry",
+                         "kernel": "esb_run_kernel", "launch_ms": launch_ms, "flop_per_replica_step": fl,
+                         "pairs_in_cut_per_step": pairs_in_cut, "pairs_listed_per_step": listed,
+                         "phase_share": {k[4:]: v / cyc_tot for k, v in cyc.items()}},
+            "clocks": sampler.summary(),
+            "failed_replicas": int(fails[0]),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference(w, args.cpu_seconds)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="box12_p3_x512", choices=sorted(WORKLOADS))
+    ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU (default: the workload's)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_native(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -784,6 +784,17 @@ int esb_get_frames(esb_handle *h, int chunk_begin, int n_chunks, double *out, in
     return ESB_OK;
 }
 
+int esb_get_frames_async(esb_handle *h, int chunk_begin, int n_chunks, double *out, void *stream)
+{
+    if (!h || !out) return fail(ESB_EINVAL, "NULL argument");
+    if (chunk_begin < 0 || n_chunks < 1 || chunk_begin + n_chunks > h->n_chunks) return fail(ESB_EINVAL, "chunk range outside the schedule");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy2DAsync(out, (size_t)n_chunks * ESB_FRAME_DOUBLES * sizeof(double),
+                         h->d_frames + (size_t)chunk_begin * ESB_FRAME_DOUBLES, (size_t)h->n_chunks * ESB_FRAME_DOUBLES * sizeof(double),
+                         (size_t)n_chunks * ESB_FRAME_DOUBLES * sizeof(double), h->R, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return ESB_OK;
+}
+
 int esb_get_status(esb_handle *h, int *status)
 {
     if (!h || !status) return fail(ESB_EINVAL, "NULL argument");

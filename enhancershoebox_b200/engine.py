@@ -71,6 +71,7 @@ _SIGNATURES = {
     "esb_sync": (C.c_int, [C.c_void_p]),
     "esb_forces": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "esb_get_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "esb_get_frames_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "esb_get_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "esb_get_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "esb_reset_counters": (C.c_int, [C.c_void_p]),

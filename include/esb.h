@@ -147,6 +147,8 @@ int esb_forces(esb_handle *h, int pair_mode, int map_id, double soft_a, int with
 /* geneTrack records: out [R][n_chunks][9] doubles (t, probe xyz*60, d_rp*60, d_rg*60, n_s5p_prom,
  * n_s5p_gene, state) (run_single_shoebox.py:1496); hist [R][n_chunks][49] ints or NULL (:1504-1519) */
 int esb_get_frames(esb_handle *h, int chunk_begin, int n_chunks, double *out, int *hist);
+/* same records, asynchronously on `stream` into a caller-pinned buffer (no histograms) */
+int esb_get_frames_async(esb_handle *h, int chunk_begin, int n_chunks, double *out, void *stream);
 int esb_get_status(esb_handle *h, int *status);                   /* [R] ESB_ST_* bits               */
 /* [R][ESB_N_COUNTERS]: force evaluations, neighbour builds, in-cutoff (ordered) pairs, listed (ordered)
  * pairs summed over evaluations, steps, total_active_steps, then SM cycles spent in the per-atom

@@ -26,6 +26,19 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def build_native() -> str:
+    """-march=native build for the CPU baseline (compiled on the machine that runs it); the ctypes
+    handle is switched to it."""
+    global _lib, _LIB_PATH
+    src = os.path.join(_HERE, "esb_oracle.c")
+    out = os.path.join(_HERE, "libesb_oracle_native.so")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src) or os.environ.get("ESB_ORACLE_REBUILD"):
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fno-fast-math", "-ffp-contract=off", "-fPIC", "-shared",
+                               "-o", out, src, "-lm"])
+    _LIB_PATH, _lib = out, None
+    return out
+
+
 def lib():
     global _lib
     if _lib is None:
