@@ -105,7 +105,7 @@ struct esb_handle {
     PairSetup *d_setups = nullptr;
     DevTab *d_tabs_closed = nullptr, *d_tabs_array = nullptr;
     float *d_tabval = nullptr, *d_tabe = nullptr;
-    unsigned short *d_nl_pool = nullptr;
+    unsigned int *d_nl_pool = nullptr;
     uint2 *d_nl_qinfo = nullptr;
     esb_chunk_desc *d_descs = nullptr;
     int *d_enh = nullptr, *d_s5p = nullptr;
@@ -167,16 +167,16 @@ int rebuild_setups(esb_handle *h)
         DevTab d;
         memset(&d, 0, sizeof(d));
         d.innersq = T.innersq; d.invdelta = 1.0 / T.delta; d.delta = (float)T.delta; d.invdelta_f = (float)(1.0 / T.delta);
-        d.poff = t * h->tlm1; d.epoff = t * h->tlm1;
-        d.plo = 0; d.phi = 0; d.p0hi = h->tlm1;
+        d.innersq_f = (float)T.innersq;
+        d.patch = 0u;                                  // empty closed-form range: every bin from the array
         d.cutsq = nextafterf((float)(T.cut * T.cut * (1.0 + 2e-7)), INFINITY);
-        d.rcsq = 0.0f; d.K = 0.0f; d.is6 = 0.0f; d.c = 1.0f;
+        d.K = 0.0f; d.is6 = 0.0f; d.c = 1.0f;
         arr[t] = d;
         eff_cut_arr[t] = T.cut;
         eff_cut_closed[t] = T.cut;
-        if (T.cf.valid) {
-            // patches = bins where the spline-built LOOKUP value departs from the closed form at the
-            // midpoint: a run at the start of the table and a run around rc
+        if (T.cf.valid && h->tlm1 < 65536) {
+            // bins where the spline-built LOOKUP value departs from the closed form at the midpoint:
+            // a run at the start of the table and a run around rc
             std::vector<char> bad(h->tlm1);
             for (int i = 0; i < h->tlm1; i++) {
                 const double mid = T.innersq + (i + 0.5) * T.delta;
@@ -184,28 +184,24 @@ int rebuild_setups(esb_handle *h)
                 bad[i] = fabs(T.f[i] - fc) > 1e-7 * (1.0 + fabs(T.f[i]));
             }
             const int irc = (int)std::min((double)h->tlm1 - 1, std::max(0.0, (T.cf.rc * T.cf.rc - T.innersq) / T.delta));
-            // low patch: from bin 0 up to the last bad bin that is followed by >= 2000 good bins before rc
-            int p0hi = 0, plo = h->tlm1, phi = 0;
-            {
-                int last_bad = -1;
-                const int stop = std::max(0, irc - 2000);
-                for (int i = 0; i < stop; i++) if (bad[i]) last_bad = i;
-                p0hi = last_bad + 1;
-                for (int i = stop; i < h->tlm1; i++) if (bad[i]) { plo = std::min(plo, i); phi = std::max(phi, i + 1); }
-                if (plo >= phi) { plo = 0; phi = 0; }
-                if (p0hi > h->tlm1 / 2) { p0hi = h->tlm1; plo = 0; phi = 0; }   // not a closed-form table after all
+            int last_bad = -1, plo = h->tlm1, phi = 0;
+            const int stop = std::max(0, irc - 2000);
+            for (int i = 0; i < stop; i++) if (bad[i]) last_bad = i;
+            const int p0hi = last_bad + 1;
+            for (int i = stop; i < h->tlm1; i++) if (bad[i]) { plo = std::min(plo, i); phi = std::max(phi, i + 1); }
+            if (p0hi <= h->tlm1 / 2 && plo > p0hi) {
+                // closed form on [p0hi, plo); everything from plo on comes from the array
+                d.patch = (unsigned int)p0hi | ((unsigned int)(plo - p0hi) << 16);
+                const double s6 = pow(T.cf.s, 6);
+                d.K = (float)(24.0 * T.cf.eps_eff / s6);
+                d.is6 = (float)(1.0 / s6);
+                d.c = (float)T.cf.c;
+                // beyond the last departing bin the table is the closed form's 0: nothing to evaluate there
+                double eff = T.cut * T.cut;
+                if (phi > 0 && T.cf.rc < T.cut) eff = std::min(eff, std::max(T.cf.rc * T.cf.rc, T.innersq + phi * T.delta));
+                d.cutsq = nextafterf((float)(eff * (1.0 + 2e-7)), INFINITY);
+                eff_cut_closed[t] = sqrt(eff);
             }
-            d.plo = plo; d.phi = phi; d.p0hi = p0hi;
-            const double s6 = pow(T.cf.s, 6);
-            d.K = (float)(24.0 * T.cf.eps_eff / s6);
-            d.is6 = (float)(1.0 / s6);
-            d.c = (float)T.cf.c;
-            d.rcsq = (float)(T.cf.rc * T.cf.rc);
-            double eff = std::max(T.cf.rc * T.cf.rc, T.innersq + phi * T.delta);
-            eff = std::min(eff, T.cut * T.cut);
-            if (p0hi == h->tlm1) eff = T.cut * T.cut;
-            d.cutsq = nextafterf((float)(eff * (1.0 + 2e-7)), INFINITY);
-            eff_cut_closed[t] = sqrt(eff);
         }
         closed[t] = d;
     }

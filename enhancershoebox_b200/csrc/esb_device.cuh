@@ -21,23 +21,23 @@
 #define ESB_N_COUNTERS 10             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases
 #define ESB_N_SETUPS 9               // 0 = pair soft, 1..4 = table maps 0..3 (closed form + patch), 5..8 = same maps, array lookups
 
-// One (KEY,cut) table.  Bins [0,p0hi) and [plo,phi) are served from the value array at poff (the
-// "patches": the first bins, where the file's r grid is too coarse for the spline to follow the
-// closed form, and the bins around rc, where the spline rings across the force jump); everywhere
-// else the closed form is evaluated at the bin midpoint.  Array-only tables have p0hi = tlm1.
-struct DevTab {
-    double innersq, invdelta;   // exact bin index: int((rsq - innersq) * invdelta)
+// One (KEY,cut) table, 48 bytes, read in the force loop as two float4 (+ two doubles on the rare
+// fp64 path).  Bins [p0hi, plo) are evaluated with the LJsoft closed form at the bin midpoint; bins
+// [0, p0hi) (the file's r grid is too coarse there for the spline to follow the closed form) and
+// [plo, tlm1) (the spline rings across the force jump at rc, then the table is ~0) are read from
+// the LOOKUP array.  Array-only tables have p0hi = plo = 0 ... i.e. an empty closed-form range.
+struct __align__(16) DevTab {
     float cutsq;                // effective cutoff^2: beyond it every bin value is 0
-    float rcsq;                 // closed form cut-off^2
+    float invdelta_f;           // fp32 bin-index estimate (verified against the bin edges, see force_phase)
+    float delta;
+    float innersq_f;
     float K;                    // 24 eps_eff / s^6
     float is6;                  // 1 / s^6
     float c;                    // alpha (1-lam)^2
-    float delta;
-    float invdelta_f;           // fp32 bin-index estimate (verified against the bin edges, see force_phase)
-    int plo, phi, poff;
-    int epoff;                  // offset of the full energy array (parity hook only)
-    int p0hi;
+    unsigned int patch;         // p0hi | (plo - p0hi) << 16
+    double innersq, invdelta;   // exact bin index: int((rsq - innersq) * invdelta)
 };
+static_assert(sizeof(DevTab) == 48, "DevTab layout is read with fixed offsets");
 
 // Per pair-style set-up: everything indexed by ti*ESB_MAXT+tj.
 struct PairSetup {
@@ -90,7 +90,7 @@ struct KArgs {
     const float *tabval;      // patch / array values (F/r), fp32
     const float *tabe;        // energy arrays (hook)
     int tlm1;
-    unsigned short *nl_pool;  // [R][ESB_NL_POOL]
+    unsigned int *nl_pool;    // [R][ESB_NL_POOL]  neighbour index | table id << 16
     uint2 *nl_qinfo;          // [R][n_pad]   per bead in cell-sorted order: {list start, atom | count << 16}
     unsigned char class_of[ESB_MAXT + 4];
     const esb_chunk_desc *descs;

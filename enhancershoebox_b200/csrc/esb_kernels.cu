@@ -160,7 +160,7 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
     const unsigned int FULL = 0xffffffffu;
     const int gl = lane & (ESB_G - 1), grp = lane / ESB_G;
     const int gshift = grp * ESB_G;
-    unsigned short *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
+    unsigned int *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
     uint2 *qinfo = a.nl_qinfo + (size_t)r * a.n_pad;
     int cursor = 0, limit = 0;
     unsigned int listed = 0;
@@ -194,6 +194,7 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
         uint4 sp = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         if (topo_i) sp = *reinterpret_cast<const uint4 *>(a.spec + (size_t)i * ESB_MAX_SPEC);
         const float *cs = S.setup->cutsq_skin + ti * ESB_MAXT;
+        const unsigned char *tabid = S.setup->tabid + ti * ESB_MAXT;
         int cnt = 0;
         int yy = y0, zz = z0;
         for (int row_i = 0; row_i < rows_max; row_i++) {
@@ -209,13 +210,13 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
             for (int k0 = 0; k0 < len_max; k0 += ESB_G) {
                 const int k = ka + k0 + gl;
                 bool ok = false;
-                int j = 0;
+                int j = 0, tj = 0;
                 if (k < kb) {
                     j = S.sidx[k];
                     const float4 pj = S.pos[j];
                     const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                     const float r2 = dx * dx + dy * dy + dz * dz;
-                    const int tj = __float_as_int(pj.w) & 0xff;
+                    tj = __float_as_int(pj.w) & 0xff;
                     ok = (r2 < cs[tj]) && (j != i);
                     if (ok && topo_i && j < a.n_topo) {
                         const unsigned int jj = (unsigned int)j;
@@ -226,7 +227,7 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
                 const unsigned int bits = (__ballot_sync(FULL, ok) >> gshift) & ((1u << ESB_G) - 1u);
                 if (ok) {
                     const int slot = cnt + __popc(bits & ((1u << gl) - 1u));
-                    if (slot < ESB_NL_MAXNB) pool[cursor + slot] = (unsigned short)j;
+                    if (slot < ESB_NL_MAXNB) pool[cursor + slot] = (unsigned int)j | ((unsigned int)tabid[tj] << 16);
                 }
                 cnt += __popc(bits);
             }
@@ -304,6 +305,34 @@ __device__ __forceinline__ void bonded_term(const Smem &S, const KArgs &a, const
 //         the bin value comes from the LOOKUP array inside the table's patch range and from the
 //         LJsoft closed form evaluated at the bin midpoint outside it (ljsoft_potential.py:10-16).
 // ------------------------------------------------------------------------------------------------
+// Rare path of the tabulated pair force (a few per cent of the in-cutoff pairs): the fp32 bin
+// estimate sits too close to a bin edge to be trusted, or the bin lies in a patch range.  The bin
+// index is recomputed in fp64 with the oracle's (unfused) operations; the value is the closed form
+// at the bin midpoint inside [p0hi, plo) and the LOOKUP array entry elsewhere.
+__device__ __noinline__ float table_pair_slow(const KArgs &a, const unsigned char *T, const unsigned int tb,
+                                              const float4 pi, const float4 pj, int *it_out)
+{
+    const float4 t0 = *reinterpret_cast<const float4 *>(T);
+    const float4 t1 = *reinterpret_cast<const float4 *>(T + 16);
+    const double innersq = *reinterpret_cast<const double *>(T + 32), invdelta = *reinterpret_cast<const double *>(T + 40);
+    const double ddx = __dsub_rn((double)pi.x, (double)pj.x), ddy = __dsub_rn((double)pi.y, (double)pj.y),
+                 ddz = __dsub_rn((double)pi.z, (double)pj.z);
+    const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
+    if (rsq < innersq) { *it_out = -1; return 0.0f; }
+    const int it = min((int)__dmul_rn(__dsub_rn(rsq, innersq), invdelta), a.tlm1 - 1);
+    *it_out = it;
+    const unsigned int patch = __float_as_uint(t1.w);
+    if ((unsigned int)(it - (int)(patch & 0xffffu)) < (patch >> 16)) {
+        const float qm = fmaf((float)it + 0.5f, t0.z, t0.w);
+        const float q2 = qm * qm;
+        const float x = fmaf(q2 * qm, t1.y, t1.z);
+        float inv = __fdividef(1.0f, x);
+        inv = inv * fmaf(-x, inv, 2.0f);
+        return t1.x * q2 * (2.0f - x) * (inv * inv * inv);
+    }
+    return a.tabval[tb * (unsigned int)a.tlm1 + it];
+}
+
 template <int MODE, bool ENERGY>
 __device__ void force_phase(const Smem &S, const KArgs &a, int r, const float soft_a, const float r0_1, const float r0_2,
                             double *energy /* [3] pair, bond, angle: per-thread partials (ENERGY only) */)
@@ -312,8 +341,9 @@ __device__ void force_phase(const Smem &S, const KArgs &a, int r, const float so
     const int tid = threadIdx.x, n = a.n_atoms;
     const int lane = tid & 31;
     const int gl = lane & (ESB_G - 1), grp = lane / ESB_G;
-    const unsigned short *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
+    const unsigned int *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
     const uint2 *qinfo = a.nl_qinfo + (size_t)r * a.n_pad;
+    const unsigned char *tabbase = reinterpret_cast<const unsigned char *>(S.tab);
     unsigned int npairs = 0;
     double e_pair = 0.0, e_bond = 0.0, e_angle = 0.0;
     // quads of the cell-sorted order, dealt round-robin to the warps; the next quad's descriptor is
@@ -330,67 +360,74 @@ __device__ void force_phase(const Smem &S, const KArgs &a, int r, const float so
         const bool valid = 4 * q + grp < n;
         const int i = (int)(qi.y & 0xffffu);
         const int cnt = valid ? (int)(qi.y >> 16) : 0;
-        const unsigned short *nl = pool + qi.x;
+        const unsigned int *nl = pool + qi.x;
         const float4 pi = S.pos[i];
-        const int ti = __float_as_int(pi.w) & 0xff;
         const int cnt_max = __reduce_max_sync(FULL, cnt);
-        const float *cutsq = S.setup->cutsq + ti * ESB_MAXT;
-        const unsigned char *tabid = S.setup->tabid + ti * ESB_MAXT;
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-        int j_next = (gl < cnt) ? nl[gl] : 0;
-        for (int e0 = 0; e0 < cnt_max; e0 += ESB_G) {
-            const int e = e0 + gl;
-            const int j = j_next;
-            j_next = (e + ESB_G < cnt) ? nl[e + ESB_G] : 0;   // prefetch: the list lives in L2
+        // The list lives in L2/HBM: four loads per lane are kept in flight (entries e, e+G, e+2G, e+3G)
+        // so that their latency overlaps the arithmetic of the entries before them.
+        auto ld = [&](int k) -> unsigned int { return (k < cnt) ? nl[k] : 0u; };
+        auto pair_body = [&](const unsigned int ent, const int e) {
             if (e < cnt) {
-                const float4 pj = S.pos[j];
+                const float4 pj = S.pos[ent & 0xffffu];
                 const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 const float r2 = dx * dx + dy * dy + dz * dz;
-                const int tj = __float_as_int(pj.w) & 0xff;
-                if (r2 < cutsq[tj]) {
-                    float fpair;
-                    if (MODE == 1) {
-                        const float rc = sqrtf(cutsq[tj]);
-                        const float rr = sqrtf(r2);
-                        const float arg = 3.14159265358979323846f * rr / rc;
-                        fpair = (rr > 0.0f) ? soft_a * sinf(arg) * 3.14159265358979323846f / rc / rr : 0.0f;
-                        if (ENERGY) e_pair += 0.5 * (double)(soft_a * (1.0f + cosf(arg)));
-                    } else {
-                        const DevTab &T = S.tab[tabid[tj]];
-                        // bin index: fp32 estimate, accepted when it is provably on the same side of
-                        // every bin edge as the exact value; otherwise recomputed in fp64 (unfused,
-                        // same operations as the oracle).
-                        const float u = (r2 - (float)T.innersq) * T.invdelta_f;
-                        int it = (int)u;
-                        const float frac = u - (float)it;
-                        const float margin = fmaf(u, 1.0e-6f, 1.0e-3f);
-                        if (!(frac > margin && frac < 1.0f - margin)) {
-                            const double ddx = __dsub_rn((double)pi.x, (double)pj.x), ddy = __dsub_rn((double)pi.y, (double)pj.y),
-                                         ddz = __dsub_rn((double)pi.z, (double)pj.z);
-                            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
-                            if (rsq < T.innersq) { atomicOr(&S.misc[M_FAIL], ESB_ST_INNER); continue; }
-                            it = (int)__dmul_rn(__dsub_rn(rsq, T.innersq), T.invdelta);
-                        }
-                        if (it < T.p0hi || (it >= T.plo && it < T.phi)) {
-                            fpair = a.tabval[T.poff + it];
-                        } else {
-                            const float q = (float)T.innersq + ((float)it + 0.5f) * T.delta;
-                            if (q < T.rcsq) {
-                                const float q2 = q * q;
-                                const float x = fmaf(q2 * q, T.is6, T.c);
-                                float inv = __fdividef(1.0f, x);
-                                inv = inv * fmaf(-x, inv, 2.0f);
-                                fpair = T.K * q2 * (2.0f - x) * (inv * inv * inv);
-                            } else {
-                                fpair = 0.0f;
-                            }
-                        }
-                        if (ENERGY) e_pair += 0.5 * (double)a.tabe[T.epoff + min(it, a.tlm1 - 1)];
+                float fpair;
+                if (MODE == 1) {
+                    const int ti = __float_as_int(pi.w) & 0xff, tj = __float_as_int(pj.w) & 0xff;
+                    const float csq = S.setup->cutsq[ti * ESB_MAXT + tj];
+                    if (!(r2 < csq)) return;
+                    const float rc = sqrtf(csq);
+                    const float rr = sqrtf(r2);
+                    const float arg = 3.14159265358979323846f * rr / rc;
+                    fpair = (rr > 0.0f) ? soft_a * sinf(arg) * 3.14159265358979323846f / rc / rr : 0.0f;
+                    if (ENERGY) e_pair += 0.5 * (double)(soft_a * (1.0f + cosf(arg)));
+                } else {
+                    // The list entry carries the table id of the pair (types are fixed between builds).
+                    // Straight-line fast path: bin index from an fp32 estimate that is accepted only when
+                    // it is provably on the same side of every bin edge as the exact value, closed form at
+                    // the bin midpoint.  Everything else (edge-near estimates, patch bins) takes the slow path.
+                    const unsigned int tb = ent >> 16;
+                    const unsigned char *T = tabbase + tb * (unsigned int)sizeof(DevTab);
+                    const float4 t0 = *reinterpret_cast<const float4 *>(T);          // cutsq, invdelta_f, delta, innersq_f
+                    const float4 t1 = *reinterpret_cast<const float4 *>(T + 16);     // K, is6, c, patch
+                    const bool acc = r2 < t0.x;
+                    const float u = (r2 - t0.w) * t0.y;
+                    int it = (int)u;
+                    const float itf = (float)it;
+                    const float frac = u - itf;
+                    const float margin = fmaf(u, 1.0e-6f, 1.0e-3f);
+                    const unsigned int patch = __float_as_uint(t1.w);            // p0hi | (plo - p0hi) << 16
+                    const bool fast = (frac > margin) && (frac < 1.0f - margin) &&
+                                      ((unsigned int)(it - (int)(patch & 0xffffu)) < (patch >> 16));
+                    const float qm = fmaf(itf + 0.5f, t0.z, t0.w);
+                    const float q2 = qm * qm;
+                    const float x = fmaf(q2 * qm, t1.y, t1.z);
+                    float inv = __fdividef(1.0f, x);
+                    inv = inv * fmaf(-x, inv, 2.0f);
+                    fpair = t1.x * q2 * (2.0f - x) * (inv * inv * inv);
+                    if (!acc) fpair = 0.0f;
+                    if (acc && !fast) {
+                        fpair = table_pair_slow(a, T, tb, pi, pj, &it);
+                        if (it < 0) { atomicOr(&S.misc[M_FAIL], ESB_ST_INNER); it = 0; }
                     }
-                    fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
-                    npairs++;
+                    npairs += acc ? 1u : 0u;
+                    if (ENERGY && acc) e_pair += 0.5 * (double)a.tabe[tb * (unsigned int)a.tlm1 + min(max(it, 0), a.tlm1 - 1)];
                 }
+                fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+                if (MODE == 1) npairs++;
             }
+        };
+        unsigned int w0 = ld(gl), w1 = ld(gl + ESB_G), w2 = ld(gl + 2 * ESB_G), w3 = ld(gl + 3 * ESB_G);
+        for (int e0 = 0; e0 < cnt_max; e0 += 4 * ESB_G) {
+            const int e = e0 + gl;
+            const unsigned int c0 = w0, c1 = w1;
+            w0 = ld(e + 4 * ESB_G); w1 = ld(e + 5 * ESB_G);
+            pair_body(c0, e); pair_body(c1, e + ESB_G);
+            if (e0 + 2 * ESB_G >= cnt_max) break;
+            const unsigned int c2 = w2, c3 = w3;
+            w2 = ld(e + 6 * ESB_G); w3 = ld(e + 7 * ESB_G);
+            pair_body(c2, e + 2 * ESB_G); pair_body(c3, e + 3 * ESB_G);
         }
         if (valid && i < a.n_topo) {
             const uint2 term = a.bterm[(size_t)gl * a.n_topo_pad + i];
