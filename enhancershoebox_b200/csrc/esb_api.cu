@@ -15,9 +15,6 @@
 
 #include "esb_device.cuh"
 
-extern "C" __global__ void esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const double delt, const double sig_nm);
-extern "C" __global__ void esb_forces_kernel(const KArgs a, const int pair_mode, const int setup_id, const float soft_a,
-                                             const int with_post, const unsigned long long eval, double *f_out, double *e_out);
 extern "C" __global__ void esb_pack_kernel(const double *x, const double *v, const int *types, const unsigned char *frozen,
                                            float4 *pos4, float4 *vel4, int n_atoms, int n_pad, int n_replicas, int replicate);
 extern "C" __global__ void esb_unpack_kernel(const float4 *pos4, const float4 *vel4, double *x, double *v, int *types,
@@ -325,7 +322,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     const size_t tot = (size_t)n_replicas * h->n_pad;
     if ((rc = dev_alloc(&h->d_pos4, tot)) || (rc = dev_alloc(&h->d_vel4, tot)) || (rc = dev_alloc(&h->d_rs, (size_t)n_replicas)) ||
         (rc = dev_alloc(&h->d_frozen, (size_t)h->n_pad)) || (rc = dev_alloc(&h->d_nl_pool, (size_t)n_replicas * ESB_NL_POOL)) ||
-        (rc = dev_alloc(&h->d_nl_qinfo, tot)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * ESB_N_COUNTERS))) {
+        (rc = dev_alloc(&h->d_nl_qinfo, 2 * tot)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * ESB_N_COUNTERS))) {
         esb_destroy(h);
         return rc;
     }
@@ -333,7 +330,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     cudaMemset(h->d_vel4, 0, tot * sizeof(float4));
     cudaMemset(h->d_frozen, 0, h->n_pad);
     cudaMemset(h->d_counters, 0, (size_t)n_replicas * ESB_N_COUNTERS * sizeof(unsigned long long));
-    cudaMemset(h->d_nl_qinfo, 0, tot * sizeof(uint2));
+    cudaMemset(h->d_nl_qinfo, 0, 2 * tot * sizeof(uint2));
     if ((rc = push_rs(h))) { esb_destroy(h); return rc; }
     // empty topology by default
     std::vector<uint2> bt((size_t)ESB_MAX_TERMS * 32, make_uint2(0, 0));
@@ -722,9 +719,7 @@ int esb_run(esb_handle *h, int chunk_begin, int n_chunks, void *stream)
     if (rc) return rc;
     KArgs k;
     fill_kargs(h, k, false);
-    CK(cudaFuncSetAttribute(esb_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    esb_run_kernel<<<h->R, ESB_THREADS, smem, (cudaStream_t)stream>>>(k, chunk_begin, n_chunks, 0.03 * 200, 60.0);
-    CK(cudaGetLastError());
+    CK(esb_launch_run(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem, (cudaStream_t)stream));
     return ESB_OK;
 }
 
@@ -752,10 +747,8 @@ int esb_forces(esb_handle *h, int pair_mode, int map_id, double soft_a, int with
     double *df = nullptr, *de = nullptr;
     CK(cudaMalloc(&df, (size_t)h->R * h->N * 3 * sizeof(double)));
     CK(cudaMalloc(&de, (size_t)h->R * 4 * sizeof(double)));
-    CK(cudaFuncSetAttribute(esb_forces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int setup_id = pair_mode == 2 ? 1 + map_id + (use_arrays ? 4 : 0) : 0;
-    esb_forces_kernel<<<h->R, ESB_THREADS, smem>>>(k, pair_mode, setup_id, (float)soft_a, with_post, eval, df, de);
-    CK(cudaGetLastError());
+    CK(esb_launch_forces(k, pair_mode, setup_id, (float)soft_a, with_post, eval, df, de, smem, 0));
     CK(cudaMemcpy(f_out, df, (size_t)h->R * h->N * 3 * sizeof(double), cudaMemcpyDeviceToHost));
     if (e_out) CK(cudaMemcpy(e_out, de, (size_t)h->R * 4 * sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(df); cudaFree(de);

@@ -91,7 +91,7 @@ struct KArgs {
     const float *tabe;        // energy arrays (hook)
     int tlm1;
     unsigned int *nl_pool;    // [R][ESB_NL_POOL]  neighbour index | table id << 16
-    uint2 *nl_qinfo;          // [R][n_pad]   per bead in cell-sorted order: {list start, atom | count << 16}
+    uint2 *nl_qinfo;          // [R][2][n_pad] {list start, atom | count << 16}: [0] sorted by list length (force order), [1] slot order (build)
     unsigned char class_of[ESB_MAXT + 4];
     const esb_chunk_desc *descs;
     // observation
@@ -123,3 +123,6 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 __device__ __forceinline__ float u32_centered(uint32_t u) { return (float)(int32_t)u * 0x1p-32f; }
 
 size_t esb_smem_bytes(int n_pad, int n_tables);
+cudaError_t esb_launch_run(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st);
+cudaError_t esb_launch_forces(const KArgs &k, int pair_mode, int setup_id, float soft_a, int with_post, unsigned long long eval,
+                              double *f_out, double *e_out, size_t smem, cudaStream_t st);

@@ -6,6 +6,9 @@
 // esb_forces_kernel   parity hook: one force evaluation (+ energies) at the stored positions.
 // esb_pack/unpack     double <-> float4 state conversion for the host-facing ABI.
 //
+// The kernels are templates on the bead capacity NP (n_pad) so that every shared-memory array
+// offset is an immediate; the phases are separate __noinline__ functions (each gets the full
+// register budget) that take the __grid_constant__ kernel arguments by reference.
 // Reference semantics (what each phase stands in for) are cited at the device functions.
 #include "esb_device.cuh"
 
@@ -14,24 +17,21 @@ namespace {
 struct Smem {
     float4 *pos;                 // x, y, z, (type | frozen << 8) as int bits
     float *vx, *vy, *vz;
-    float *fx, *fy, *fz;         // forces; the same bytes serve as cell-list scratch during a build
+    float *fx, *fy, *fz;         // forces; the same bytes serve as scratch during a list build
     float *bx, *by, *bz;         // positions at the last neighbour build
     PairSetup *setup;
     DevTab *tab;
     int *misc;                   // see M_* below
     double *dmisc;
     // aliases into the force region, valid only inside build_lists()
-    unsigned short *cend;        // [ncells + 2]  inclusive prefix: end offset of every cell
-    unsigned short *sidx;        // [n_pad]       atom indices sorted by cell
+    unsigned short *cend;        // [nslots + 2]  running end offset of every slot
+    unsigned short *sidx;        // [n_pad]       atom indices sorted by slot
 };
 
-enum { M_WORK = 0, M_WORK2, M_POOLCUR, M_FAIL, M_PAIRS, M_CURLIST, M_SCAN /* 8 warps */,
+enum { M_POOLCUR = 0, M_FAIL, M_PAIRS, M_CURLIST, M_SCAN /* 8 warps */,
        M_CNT_PROM = M_SCAN + 8, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */, M_END = M_HIST + 52 };
-static_assert(ESB_MAX_TERMS == ESB_G, "one bonded term per lane of a group");
 static_assert(ESB_THREADS == 256, "scan scratch assumes 8 warps");
 enum { D_RR = 0, D_PROBE = 3, D_GENE = 6, D_END = 10 };
-
-__device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables)
 {
@@ -45,9 +45,14 @@ __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables)
     return (b + 15) & ~(size_t)15;
 }
 
-__device__ __forceinline__ void carve(unsigned char *base, const KArgs &a, Smem &S)
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+template <int NP>
+__device__ __forceinline__ Smem carve(const KArgs &a)
 {
-    const int np = a.n_pad;
+    const int np = NP ? NP : a.n_pad;   // compile-time bead capacity: every array offset is an immediate
+    Smem S;
+    unsigned char *base = smem_raw;
     size_t o = 0;
     S.pos = reinterpret_cast<float4 *>(base + o); o += (size_t)np * 16;
     S.vx = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
@@ -59,19 +64,13 @@ __device__ __forceinline__ void carve(unsigned char *base, const KArgs &a, Smem 
     S.bx = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.by = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.bz = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
-    S.setup = reinterpret_cast<PairSetup *>(base + o); o += align16(sizeof(PairSetup));
-    S.tab = reinterpret_cast<DevTab *>(base + o); o += align16((size_t)a.n_tables * sizeof(DevTab));
+    S.setup = reinterpret_cast<PairSetup *>(base + o); o += (sizeof(PairSetup) + 15) & ~(size_t)15;
+    S.tab = reinterpret_cast<DevTab *>(base + o); o += ((size_t)a.n_tables * sizeof(DevTab) + 15) & ~(size_t)15;
     S.dmisc = reinterpret_cast<double *>(base + o); o += (size_t)D_END * 8;
     S.misc = reinterpret_cast<int *>(base + o);
     S.cend = reinterpret_cast<unsigned short *>(S.fx);
     S.sidx = S.cend + ((a.ncells * ESB_NCLASS + 2 + 7) & ~7);
-}
-
-__device__ __forceinline__ void load_setup(const Smem &S, const KArgs &a, int setup_id)
-{
-    const int *src = reinterpret_cast<const int *>(a.setups + setup_id);
-    int *dst = reinterpret_cast<int *>(S.setup);
-    for (int k = threadIdx.x; k < (int)(sizeof(PairSetup) / 4); k += ESB_THREADS) dst[k] = src[k];
+    return S;
 }
 
 __device__ __forceinline__ int cell_coord(float x, float lo, float inv, int n)
@@ -80,18 +79,6 @@ __device__ __forceinline__ int cell_coord(float x, float lo, float inv, int n)
     return min(max(c, 0), n - 1);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Neighbour list build.  Stands in for LAMMPS' binned neighbour build (`neighbor 0.3 multi`,
-// `neigh_modify every 1 delay 10 check yes`, run_single_shoebox.py:532-533): per-type-pair
-// cutoff + skin, 1-2/1-3/1-4 partners excluded (default special_bonds).  Full list (both i->j and
-// j->i) so the force loop needs no scatter.
-//
-// Beads are counting-sorted into slots = (cell, species class); inside a slot they are ordered by
-// atom index, so the result is deterministic.  The sorted order is also the processing order of
-// both the build and the force loop: four consecutive beads (a "quad": same cell, same class,
-// hence near-identical candidate ranges and list lengths) share a warp, one per group of ESB_G
-// lanes, and run in lock step.
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int slot_of(const KArgs &a, const float4 p)
 {
     const int cx = cell_coord(p.x, a.lo[0], a.cell_inv, a.ncx);
@@ -100,8 +87,22 @@ __device__ __forceinline__ int slot_of(const KArgs &a, const float4 p)
     return ((cz * a.ncy + cy) * a.ncx + cx) * ESB_NCLASS + a.class_of[__float_as_int(p.w) & 0xff];
 }
 
-__device__ void build_lists(const Smem &S, const KArgs &a, int r)
+// ------------------------------------------------------------------------------------------------
+// Neighbour list build.  Stands in for LAMMPS' binned neighbour build (`neighbor 0.3 multi`,
+// `neigh_modify every 1 delay 10 check yes`, run_single_shoebox.py:532-533): per-type-pair
+// cutoff + skin, 1-2/1-3/1-4 partners excluded (default special_bonds).  Full list (both i->j and
+// j->i) so the force loop needs no scatter; every entry carries the pair's table id.
+//
+// Beads are counting-sorted into slots = (cell, species class); inside a slot they are ordered by
+// atom index, so every bead's list is deterministic.  The build walks the slot order four beads
+// ("quad": same cell, same class, hence near-identical candidate ranges) per warp, one per group of
+// ESB_G lanes, in lock step.  Afterwards the descriptors are re-sorted by list length: that is the
+// order in which the force loop forms its quads, so that the four lists of a quad end together.
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__device__ __noinline__ void build_lists(const KArgs &a, const int r)
 {
+    const Smem S = carve<NP>(a);
     const int tid = threadIdx.x, n = a.n_atoms;
     const int lane = tid & 31, warp = tid >> 5;
     const int nslots = a.ncells * ESB_NCLASS;
@@ -161,7 +162,9 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
     const int gl = lane & (ESB_G - 1), grp = lane / ESB_G;
     const int gshift = grp * ESB_G;
     unsigned int *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
-    uint2 *qinfo = a.nl_qinfo + (size_t)r * a.n_pad;
+    uint2 *qbuild = a.nl_qinfo + ((size_t)r * 2 + 1) * a.n_pad;     // descriptors in build (slot) order
+    const float lox = a.lo[0], loy = a.lo[1], loz = a.lo[2], cinv = a.cell_inv;
+    const int ncx = a.ncx, ncy = a.ncy, ncz = a.ncz, n_topo = a.n_topo;
     int cursor = 0, limit = 0;
     unsigned int listed = 0;
     const int nquads = (n + 3) >> 2;
@@ -182,25 +185,26 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
         const float4 pi = S.pos[i];
         const int ti = __float_as_int(pi.w) & 0xff;
         const int rng = S.setup->range[ti];
-        const int cx = cell_coord(pi.x, a.lo[0], a.cell_inv, a.ncx);
-        const int cy = cell_coord(pi.y, a.lo[1], a.cell_inv, a.ncy);
-        const int cz = cell_coord(pi.z, a.lo[2], a.cell_inv, a.ncz);
-        const int x0 = max(cx - rng, 0), x1 = min(cx + rng, a.ncx - 1);
-        const int y0 = max(cy - rng, 0), y1 = min(cy + rng, a.ncy - 1);
-        const int z0 = max(cz - rng, 0), z1 = min(cz + rng, a.ncz - 1);
+        const int cx = cell_coord(pi.x, lox, cinv, ncx);
+        const int cy = cell_coord(pi.y, loy, cinv, ncy);
+        const int cz = cell_coord(pi.z, loz, cinv, ncz);
+        const int x0 = max(cx - rng, 0), x1 = min(cx + rng, ncx - 1);
+        const int y0 = max(cy - rng, 0), y1 = min(cy + rng, ncy - 1);
+        const int z0 = max(cz - rng, 0), z1 = min(cz + rng, ncz - 1);
         const int nrows = valid ? (y1 - y0 + 1) * (z1 - z0 + 1) : 0;
         const int rows_max = __reduce_max_sync(FULL, nrows);
-        const bool topo_i = i < a.n_topo;
+        const bool topo_i = i < n_topo;
         uint4 sp = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         if (topo_i) sp = *reinterpret_cast<const uint4 *>(a.spec + (size_t)i * ESB_MAX_SPEC);
         const float *cs = S.setup->cutsq_skin + ti * ESB_MAXT;
         const unsigned char *tabid = S.setup->tabid + ti * ESB_MAXT;
+        unsigned int *out = pool + cursor;
         int cnt = 0;
         int yy = y0, zz = z0;
         for (int row_i = 0; row_i < rows_max; row_i++) {
             int ka = 0, kb = 0;
             if (row_i < nrows) {
-                const int row = (zz * a.ncy + yy) * a.ncx;
+                const int row = (zz * ncy + yy) * ncx;
                 const int s_first = (row + x0) * ESB_NCLASS;
                 ka = s_first ? S.cend[s_first - 1] : 0;
                 kb = S.cend[(row + x1) * ESB_NCLASS + ESB_NCLASS - 1];
@@ -210,15 +214,16 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
             for (int k0 = 0; k0 < len_max; k0 += ESB_G) {
                 const int k = ka + k0 + gl;
                 bool ok = false;
-                int j = 0, tj = 0;
+                unsigned int ent = 0u;
                 if (k < kb) {
-                    j = S.sidx[k];
+                    const int j = S.sidx[k];
                     const float4 pj = S.pos[j];
                     const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                     const float r2 = dx * dx + dy * dy + dz * dz;
-                    tj = __float_as_int(pj.w) & 0xff;
+                    const int tj = __float_as_int(pj.w) & 0xff;
                     ok = (r2 < cs[tj]) && (j != i);
-                    if (ok && topo_i && j < a.n_topo) {
+                    ent = (unsigned int)j | ((unsigned int)tabid[tj] << 16);
+                    if (ok && topo_i && j < n_topo) {
                         const unsigned int jj = (unsigned int)j;
                         ok = !((sp.x & 0xffffu) == jj || (sp.x >> 16) == jj || (sp.y & 0xffffu) == jj || (sp.y >> 16) == jj ||
                                (sp.z & 0xffffu) == jj || (sp.z >> 16) == jj || (sp.w & 0xffffu) == jj || (sp.w >> 16) == jj);
@@ -227,7 +232,7 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
                 const unsigned int bits = (__ballot_sync(FULL, ok) >> gshift) & ((1u << ESB_G) - 1u);
                 if (ok) {
                     const int slot = cnt + __popc(bits & ((1u << gl) - 1u));
-                    if (slot < ESB_NL_MAXNB) pool[cursor + slot] = (unsigned int)j | ((unsigned int)tabid[tj] << 16);
+                    if (slot < ESB_NL_MAXNB) out[slot] = ent;
                 }
                 cnt += __popc(bits);
             }
@@ -237,117 +242,140 @@ __device__ void build_lists(const Smem &S, const KArgs &a, int r)
             cnt = ESB_NL_MAXNB;
         }
         if (!valid) cnt = 0;
-        if (idx < a.n_pad && gl == 0) { qinfo[idx] = make_uint2((unsigned int)cursor, (unsigned int)i | ((unsigned int)cnt << 16)); listed += cnt; }
+        if (idx < a.n_pad && gl == 0) { qbuild[idx] = make_uint2((unsigned int)cursor, (unsigned int)i | ((unsigned int)cnt << 16)); listed += cnt; }
         cursor += cnt;
     }
     if (listed) atomicAdd(&S.misc[M_CURLIST], (int)listed);
+    __syncthreads();
+    // ---- force order: descriptors sorted by decreasing list length (counting sort on the length) ----
+    {
+        uint2 *qforce = a.nl_qinfo + (size_t)r * 2 * a.n_pad;
+        int *hist = reinterpret_cast<int *>(S.fx);                 // 1024 counters; the scratch is free again
+        for (int k = tid; k < ESB_NL_MAXNB + 1; k += ESB_THREADS) hist[k] = 0;
+        __syncthreads();
+        for (int k = tid; k < n; k += ESB_THREADS) atomicAdd(&hist[ESB_NL_MAXNB - (int)(qbuild[k].y >> 16)], 1);
+        __syncthreads();
+        // exclusive scan of 1024 counters: 4 per thread
+        int v[4], s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = hist[4 * tid + k]; s += v[k]; }
+        int incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) S.misc[M_SCAN + warp] = incl;
+        __syncthreads();
+        int base = incl - s;
+        for (int w = 0; w < warp; w++) base += S.misc[M_SCAN + w];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { hist[4 * tid + k] = base; base += v[k]; }
+        __syncthreads();
+        for (int k = tid; k < n; k += ESB_THREADS) {
+            const uint2 d = qbuild[k];
+            qforce[atomicAdd(&hist[ESB_NL_MAXNB - (int)(d.y >> 16)], 1)] = d;
+        }
+    }
     __syncthreads();   // lists (global) and the scratch alias are settled before forces are written
 }
 
 // ------------------------------------------------------------------------------------------------
-// Bonded terms of one atom (gathered per atom so that no force is ever scattered):
+// Bonded forces, one thread per bonded bead, written to S.f* before the pair loop adds to them.
+// Every bead's terms are stored kind-major (bonds, then angle ends, then the angle it is the vertex
+// of), so all threads of a warp evaluate the same kind in the same pass.
 // [LAMMPS-ext] BondHarmonic::compute  E = K (r - r0)^2       (bond_coeff, run_single_shoebox.py:632-633)
 // [LAMMPS-ext] AngleCosine::compute   E = K (1 + cos theta)  (angle_coeff, run_single_shoebox.py:583-584)
 // ------------------------------------------------------------------------------------------------
 template <bool ENERGY>
-__device__ __forceinline__ void bonded_term(const Smem &S, const KArgs &a, const float4 pi, uint2 term,
-                                            const float r0_1, const float r0_2,
-                                            float &fx, float &fy, float &fz, double &e_bond, double &e_angle)
+__device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, const float r0_1, const float r0_2,
+                                              double &e_bond, double &e_angle)
 {
-    const int kind = term.y & 0xff, type = (term.y >> 8) & 0xff;
-    if (kind == 0) return;
-    const float4 pa = S.pos[term.x & 0xffffu];
-    if (kind == 1) {
-        const float dx = pi.x - pa.x, dy = pi.y - pa.y, dz = pi.z - pa.z;
-        const float r = sqrtf(dx * dx + dy * dy + dz * dz);
-        const float dr = r - (type == 1 ? r0_1 : r0_2);
-        const float rk = a.bond_k[type] * dr;
-        const float fb = (r > 0.0f) ? -2.0f * rk / r : 0.0f;
-        fx += dx * fb; fy += dy * fb; fz += dz * fb;
-        if (ENERGY) e_bond += 0.5 * (double)(rk * dr);   // each bond is visited from both ends
-        return;
-    }
-    const float4 pb = S.pos[term.x >> 16];
-    const float k = a.angle_k[type];
-    if (kind == 2) {
-        // this atom is an end (i1); pa = vertex (i2), pb = other end (i3)
-        const float d1x = pi.x - pa.x, d1y = pi.y - pa.y, d1z = pi.z - pa.z;
-        const float d2x = pb.x - pa.x, d2y = pb.y - pa.y, d2z = pb.z - pa.z;
-        const float rsq1 = d1x * d1x + d1y * d1y + d1z * d1z, rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
-        const float r1r2 = sqrtf(rsq1) * sqrtf(rsq2);
-        float c = (d1x * d2x + d1y * d2y + d1z * d2z) / r1r2;
-        c = fminf(fmaxf(c, -1.0f), 1.0f);
-        const float a11 = k * c / rsq1, a12 = -k / r1r2;
-        fx += a11 * d1x + a12 * d2x; fy += a11 * d1y + a12 * d2y; fz += a11 * d1z + a12 * d2z;
-    } else {
-        // this atom is the vertex (i2); pa = i1, pb = i3
-        const float d1x = pa.x - pi.x, d1y = pa.y - pi.y, d1z = pa.z - pi.z;
-        const float d2x = pb.x - pi.x, d2y = pb.y - pi.y, d2z = pb.z - pi.z;
-        const float rsq1 = d1x * d1x + d1y * d1y + d1z * d1z, rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
-        const float r1r2 = sqrtf(rsq1) * sqrtf(rsq2);
-        float c = (d1x * d2x + d1y * d2y + d1z * d2z) / r1r2;
-        c = fminf(fmaxf(c, -1.0f), 1.0f);
-        const float a11 = k * c / rsq1, a12 = -k / r1r2, a22 = k * c / rsq2;
-        fx -= (a11 * d1x + a12 * d2x) + (a22 * d2x + a12 * d1x);
-        fy -= (a11 * d1y + a12 * d2y) + (a22 * d2y + a12 * d1y);
-        fz -= (a11 * d1z + a12 * d2z) + (a22 * d2z + a12 * d1z);
-        if (ENERGY) e_angle += (double)(k * (1.0f + c));
+    const int n = a.n_atoms, n_topo = a.n_topo, ntp = a.n_topo_pad;
+    for (int i = threadIdx.x; i < n; i += ESB_THREADS) {
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        if (i < n_topo) {
+            const float4 pi = S.pos[i];
+#pragma unroll 1
+            for (int t = 0; t < ESB_MAX_TERMS; t++) {
+                const uint2 term = a.bterm[(size_t)t * ntp + i];
+                const int kind = term.y & 0xff, type = (term.y >> 8) & 0xff;
+                if (kind == 0) continue;
+                const float4 pa = S.pos[term.x & 0xffffu];
+                if (kind == 1) {
+                    const float dx = pi.x - pa.x, dy = pi.y - pa.y, dz = pi.z - pa.z;
+                    const float rr = sqrtf(dx * dx + dy * dy + dz * dz);
+                    const float dr = rr - (type == 1 ? r0_1 : r0_2);
+                    const float rk = a.bond_k[type] * dr;
+                    const float fb = (rr > 0.0f) ? -2.0f * rk / rr : 0.0f;
+                    fx += dx * fb; fy += dy * fb; fz += dz * fb;
+                    if (ENERGY) e_bond += 0.5 * (double)(rk * dr);   // each bond is visited from both ends
+                    continue;
+                }
+                const float4 pb = S.pos[term.x >> 16];
+                const float k = a.angle_k[type];
+                if (kind == 2) {
+                    // this bead is an end (i1); pa = vertex (i2), pb = other end (i3)
+                    const float d1x = pi.x - pa.x, d1y = pi.y - pa.y, d1z = pi.z - pa.z;
+                    const float d2x = pb.x - pa.x, d2y = pb.y - pa.y, d2z = pb.z - pa.z;
+                    const float rsq1 = d1x * d1x + d1y * d1y + d1z * d1z, rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
+                    const float r1r2 = sqrtf(rsq1) * sqrtf(rsq2);
+                    float c = (d1x * d2x + d1y * d2y + d1z * d2z) / r1r2;
+                    c = fminf(fmaxf(c, -1.0f), 1.0f);
+                    const float a11 = k * c / rsq1, a12 = -k / r1r2;
+                    fx += a11 * d1x + a12 * d2x; fy += a11 * d1y + a12 * d2y; fz += a11 * d1z + a12 * d2z;
+                } else {
+                    // this bead is the vertex (i2); pa = i1, pb = i3
+                    const float d1x = pa.x - pi.x, d1y = pa.y - pi.y, d1z = pa.z - pi.z;
+                    const float d2x = pb.x - pi.x, d2y = pb.y - pi.y, d2z = pb.z - pi.z;
+                    const float rsq1 = d1x * d1x + d1y * d1y + d1z * d1z, rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
+                    const float r1r2 = sqrtf(rsq1) * sqrtf(rsq2);
+                    float c = (d1x * d2x + d1y * d2y + d1z * d2z) / r1r2;
+                    c = fminf(fmaxf(c, -1.0f), 1.0f);
+                    const float a11 = k * c / rsq1, a12 = -k / r1r2, a22 = k * c / rsq2;
+                    fx -= (a11 * d1x + a12 * d2x) + (a22 * d2x + a12 * d1x);
+                    fy -= (a11 * d1y + a12 * d2y) + (a22 * d2y + a12 * d1y);
+                    fz -= (a11 * d1z + a12 * d2z) + (a22 * d2z + a12 * d1z);
+                    if (ENERGY) e_angle += (double)(k * (1.0f + c));
+                }
+            }
+        }
+        S.fx[i] = fx; S.fy[i] = fy; S.fz[i] = fz;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Force evaluation: pair (soft or tabulated) + bonded, gathered per atom by a group of ESB_G lanes.
+// Force evaluation: bonded prologue, then the pair loop gathered per bead by a group of ESB_G lanes.
 //
 // MODE 1  [LAMMPS-ext] PairSoft::compute   E = A [1 + cos(pi r / rc)]   (run_single_shoebox.py:589-628)
 // MODE 2  [LAMMPS-ext] PairTable::compute, tabstyle LOOKUP: itable = int((rsq - innersq) * invdelta),
-//         fpair = f[itable] (run_single_shoebox.py:800-874).  The bin index is computed in fp64 from
-//         the fp32 coordinates with the same (unfused) operations as the oracle, so it is bit-exact;
-//         the bin value comes from the LOOKUP array inside the table's patch range and from the
-//         LJsoft closed form evaluated at the bin midpoint outside it (ljsoft_potential.py:10-16).
+//         fpair = f[itable] (run_single_shoebox.py:800-874).  The bin index comes from an fp32
+//         estimate that is accepted only when it is provably on the same side of every bin edge as
+//         the exact value, and is otherwise recomputed in fp64 from the fp32 coordinates with the
+//         oracle's (unfused) operations: it is bit-exact.  The bin value is the LJsoft closed form at
+//         the bin midpoint (ljsoft_potential.py:10-16) inside [p0hi, plo) and the LOOKUP array
+//         entry elsewhere.
 // ------------------------------------------------------------------------------------------------
-// Rare path of the tabulated pair force (a few per cent of the in-cutoff pairs): the fp32 bin
-// estimate sits too close to a bin edge to be trusted, or the bin lies in a patch range.  The bin
-// index is recomputed in fp64 with the oracle's (unfused) operations; the value is the closed form
-// at the bin midpoint inside [p0hi, plo) and the LOOKUP array entry elsewhere.
-__device__ __noinline__ float table_pair_slow(const KArgs &a, const unsigned char *T, const unsigned int tb,
-                                              const float4 pi, const float4 pj, int *it_out)
+template <int NP, int MODE, bool ENERGY>
+__device__ __noinline__ void force_phase(const KArgs &a, const int r, const float soft_a, const float r0_1, const float r0_2,
+                                         double *energy /* [3] pair, bond, angle: per-thread partials (ENERGY only) */)
 {
-    const float4 t0 = *reinterpret_cast<const float4 *>(T);
-    const float4 t1 = *reinterpret_cast<const float4 *>(T + 16);
-    const double innersq = *reinterpret_cast<const double *>(T + 32), invdelta = *reinterpret_cast<const double *>(T + 40);
-    const double ddx = __dsub_rn((double)pi.x, (double)pj.x), ddy = __dsub_rn((double)pi.y, (double)pj.y),
-                 ddz = __dsub_rn((double)pi.z, (double)pj.z);
-    const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
-    if (rsq < innersq) { *it_out = -1; return 0.0f; }
-    const int it = min((int)__dmul_rn(__dsub_rn(rsq, innersq), invdelta), a.tlm1 - 1);
-    *it_out = it;
-    const unsigned int patch = __float_as_uint(t1.w);
-    if ((unsigned int)(it - (int)(patch & 0xffffu)) < (patch >> 16)) {
-        const float qm = fmaf((float)it + 0.5f, t0.z, t0.w);
-        const float q2 = qm * qm;
-        const float x = fmaf(q2 * qm, t1.y, t1.z);
-        float inv = __fdividef(1.0f, x);
-        inv = inv * fmaf(-x, inv, 2.0f);
-        return t1.x * q2 * (2.0f - x) * (inv * inv * inv);
-    }
-    return a.tabval[tb * (unsigned int)a.tlm1 + it];
-}
-
-template <int MODE, bool ENERGY>
-__device__ void force_phase(const Smem &S, const KArgs &a, int r, const float soft_a, const float r0_1, const float r0_2,
-                            double *energy /* [3] pair, bond, angle: per-thread partials (ENERGY only) */)
-{
+    const Smem S = carve<NP>(a);
     const unsigned int FULL = 0xffffffffu;
     const int tid = threadIdx.x, n = a.n_atoms;
     const int lane = tid & 31;
     const int gl = lane & (ESB_G - 1), grp = lane / ESB_G;
-    const unsigned int *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
-    const uint2 *qinfo = a.nl_qinfo + (size_t)r * a.n_pad;
-    const unsigned char *tabbase = reinterpret_cast<const unsigned char *>(S.tab);
-    unsigned int npairs = 0;
     double e_pair = 0.0, e_bond = 0.0, e_angle = 0.0;
-    // quads of the cell-sorted order, dealt round-robin to the warps; the next quad's descriptor is
-    // fetched (L2) while the current one is processed
+    bonded_forces<ENERGY>(S, a, r0_1, r0_2, e_bond, e_angle);
+    __syncthreads();
+    const unsigned int *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
+    const uint2 *qinfo = a.nl_qinfo + (size_t)r * 2 * a.n_pad;
+    const unsigned char *tabbase = reinterpret_cast<const unsigned char *>(S.tab);
+    const float *tabval = a.tabval;
+    const int tlm1 = a.tlm1;
+    unsigned int npairs = 0;
+    // quads in order of decreasing list length, dealt round-robin to the warps; the next quad's
+    // descriptor is fetched (L2) while the current one is processed
     const int nquads = (n + 3) >> 2;
     const int warp = tid >> 5;
     uint2 qi_next = make_uint2(0u, 0u);
@@ -377,45 +405,45 @@ __device__ void force_phase(const Smem &S, const KArgs &a, int r, const float so
                     const int ti = __float_as_int(pi.w) & 0xff, tj = __float_as_int(pj.w) & 0xff;
                     const float csq = S.setup->cutsq[ti * ESB_MAXT + tj];
                     if (!(r2 < csq)) return;
-                    const float rc = sqrtf(csq);
+                    const float irc = rsqrtf(csq);
                     const float rr = sqrtf(r2);
-                    const float arg = 3.14159265358979323846f * rr / rc;
-                    fpair = (rr > 0.0f) ? soft_a * sinf(arg) * 3.14159265358979323846f / rc / rr : 0.0f;
-                    if (ENERGY) e_pair += 0.5 * (double)(soft_a * (1.0f + cosf(arg)));
+                    const float xr = rr * irc;                               // r / rc in [0, 1)
+                    fpair = (rr > 0.0f) ? soft_a * sinpif(xr) * 3.14159265358979323846f * irc / rr : 0.0f;
+                    if (ENERGY) e_pair += 0.5 * (double)(soft_a * (1.0f + cospif(xr)));
+                    npairs++;
                 } else {
-                    // The list entry carries the table id of the pair (types are fixed between builds).
-                    // Straight-line fast path: bin index from an fp32 estimate that is accepted only when
-                    // it is provably on the same side of every bin edge as the exact value, closed form at
-                    // the bin midpoint.  Everything else (edge-near estimates, patch bins) takes the slow path.
-                    const unsigned int tb = ent >> 16;
+                    const unsigned int tb = ent >> 16;                          // table id of the pair (fixed between builds)
                     const unsigned char *T = tabbase + tb * (unsigned int)sizeof(DevTab);
                     const float4 t0 = *reinterpret_cast<const float4 *>(T);          // cutsq, invdelta_f, delta, innersq_f
+                    if (!(r2 < t0.x)) return;
                     const float4 t1 = *reinterpret_cast<const float4 *>(T + 16);     // K, is6, c, patch
-                    const bool acc = r2 < t0.x;
                     const float u = (r2 - t0.w) * t0.y;
                     int it = (int)u;
-                    const float itf = (float)it;
-                    const float frac = u - itf;
-                    const float margin = fmaf(u, 1.0e-6f, 1.0e-3f);
+                    const float frac = u - (float)it;
+                    // |u - u_exact| <= 8 ulp-relative (dx: 1, squares+sums: 5, offset+scale: 2) = 4.8e-7 u
+                    const float margin = fmaf(u, 5.0e-7f, 1.0e-4f);
+                    if (!(frac > margin && frac < 1.0f - margin)) {
+                        const double innersq = *reinterpret_cast<const double *>(T + 32), invdelta = *reinterpret_cast<const double *>(T + 40);
+                        const double ddx = __dsub_rn((double)pi.x, (double)pj.x), ddy = __dsub_rn((double)pi.y, (double)pj.y),
+                                     ddz = __dsub_rn((double)pi.z, (double)pj.z);
+                        const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
+                        if (rsq < innersq) { atomicOr(&S.misc[M_FAIL], ESB_ST_INNER); return; }
+                        it = min((int)__dmul_rn(__dsub_rn(rsq, innersq), invdelta), tlm1 - 1);
+                    }
                     const unsigned int patch = __float_as_uint(t1.w);            // p0hi | (plo - p0hi) << 16
-                    const bool fast = (frac > margin) && (frac < 1.0f - margin) &&
-                                      ((unsigned int)(it - (int)(patch & 0xffffu)) < (patch >> 16));
-                    const float qm = fmaf(itf + 0.5f, t0.z, t0.w);
+                    const bool closed = (unsigned int)(it - (int)(patch & 0xffffu)) < (patch >> 16);
+                    // closed form at the bin midpoint (bins [p0hi, plo) lie below rc)
+                    const float qm = fmaf((float)it + 0.5f, t0.z, t0.w);
                     const float q2 = qm * qm;
                     const float x = fmaf(q2 * qm, t1.y, t1.z);
                     float inv = __fdividef(1.0f, x);
                     inv = inv * fmaf(-x, inv, 2.0f);
                     fpair = t1.x * q2 * (2.0f - x) * (inv * inv * inv);
-                    if (!acc) fpair = 0.0f;
-                    if (acc && !fast) {
-                        fpair = table_pair_slow(a, T, tb, pi, pj, &it);
-                        if (it < 0) { atomicOr(&S.misc[M_FAIL], ESB_ST_INNER); it = 0; }
-                    }
-                    npairs += acc ? 1u : 0u;
-                    if (ENERGY && acc) e_pair += 0.5 * (double)a.tabe[tb * (unsigned int)a.tlm1 + min(max(it, 0), a.tlm1 - 1)];
+                    if (!closed) fpair = tabval[tb * (unsigned int)tlm1 + it];   // predicated load: patch bins are rare
+                    if (ENERGY) e_pair += 0.5 * (double)a.tabe[tb * (unsigned int)tlm1 + it];
+                    npairs++;
                 }
                 fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
-                if (MODE == 1) npairs++;
             }
         };
         unsigned int w0 = ld(gl), w1 = ld(gl + ESB_G), w2 = ld(gl + 2 * ESB_G), w3 = ld(gl + 3 * ESB_G);
@@ -429,17 +457,13 @@ __device__ void force_phase(const Smem &S, const KArgs &a, int r, const float so
             w2 = ld(e + 6 * ESB_G); w3 = ld(e + 7 * ESB_G);
             pair_body(c2, e + 2 * ESB_G); pair_body(c3, e + 3 * ESB_G);
         }
-        if (valid && i < a.n_topo) {
-            const uint2 term = a.bterm[(size_t)gl * a.n_topo_pad + i];
-            bonded_term<ENERGY>(S, a, pi, term, r0_1, r0_2, fx, fy, fz, e_bond, e_angle);
-        }
 #pragma unroll
         for (int d = ESB_G >> 1; d >= 1; d >>= 1) {
             fx += __shfl_xor_sync(FULL, fx, d);
             fy += __shfl_xor_sync(FULL, fy, d);
             fz += __shfl_xor_sync(FULL, fz, d);
         }
-        if (valid && gl == 0) { S.fx[i] = fx; S.fy[i] = fy; S.fz[i] = fz; }
+        if (valid && gl == 0) { S.fx[i] += fx; S.fy[i] += fy; S.fz[i] += fz; }
     }
     if (npairs) atomicAdd(&S.misc[M_PAIRS], (int)npairs);
     if (ENERGY) { energy[0] += e_pair; energy[1] += e_bond; energy[2] += e_angle; }
@@ -497,9 +521,11 @@ __device__ __forceinline__ int post_force(const KArgs &a, int i, const float4 p,
 // Returns non-zero when this thread saw a bead move further than skin/2 since the last build;
 // failures (wall crossing, non-finite values) are OR-ed into S.misc[M_FAIL].
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int atom_phase(const Smem &S, const KArgs &a, const bool do_final, const bool do_initial,
-                                          const uint32_t k0, const uint32_t k1, const unsigned long long eval)
+template <int NP>
+__device__ __noinline__ int atom_phase(const KArgs &a, const bool do_final, const bool do_initial,
+                                       const uint32_t k0, const uint32_t k1, const unsigned long long eval)
 {
+    const Smem S = carve<NP>(a);
     int flags = 0;
     const float dtf = 0.5f * a.dt, dtv = a.dt;
     double dummy = 0.0;
@@ -542,8 +568,10 @@ __device__ __forceinline__ double dist_sq3(const double ax, const double ay, con
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-__device__ void observe(const Smem &S, const KArgs &a, int r, const esb_chunk_desc &d, ReplicaScalars &rs, double delt, double sig_nm, int slot)
+template <int NP>
+__device__ __noinline__ void observe(const KArgs &a, int r, const esb_chunk_desc &d, ReplicaScalars &rs, double delt, double sig_nm, int slot)
 {
+    const Smem S = carve<NP>(a);
     const int tid = threadIdx.x;
     const Layout L = a.lay;
     const int probe = L.gene_start - L.promoter_length + 2;
@@ -669,22 +697,23 @@ __device__ void observe(const Smem &S, const KArgs &a, int r, const esb_chunk_de
     __syncthreads();
 }
 
+
 }  // namespace
 
 // ================================================================================================
-extern "C" __global__ void __launch_bounds__(ESB_THREADS, 3)
-esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const double delt, const double sig_nm)
+template <int NP>
+__global__ void __launch_bounds__(ESB_THREADS, 3)
+esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int n_chunks, const double delt, const double sig_nm)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem S;
-    carve(smem_raw, a, S);
+    const Smem S = carve<NP>(a);
     const int r = blockIdx.x, tid = threadIdx.x;
+    const int np = NP ? NP : a.n_pad;
     ReplicaScalars rs = a.rs[r];
     if (rs.status != 0) return;   // a failed replica no longer advances (LAMMPS would have aborted)
 
-    for (int k = tid; k < a.n_pad; k += ESB_THREADS) {
-        S.pos[k] = a.pos4[(size_t)r * a.n_pad + k];
-        const float4 v = a.vel4[(size_t)r * a.n_pad + k];
+    for (int k = tid; k < np; k += ESB_THREADS) {
+        S.pos[k] = a.pos4[(size_t)r * np + k];
+        const float4 v = a.vel4[(size_t)r * np + k];
         S.vx[k] = v.x; S.vy[k] = v.y; S.vz[k] = v.z;
     }
     for (int k = tid; k < a.n_tables * (int)(sizeof(DevTab) / 4); k += ESB_THREADS)
@@ -699,8 +728,13 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
     for (int c = chunk_begin; c < chunk_begin + n_chunks && !failed; c++) {
         const esb_chunk_desc d = a.descs[c];
         __syncthreads();
-        load_setup(S, a, d.pair_mode == 1 ? 0 : 1 + d.map_id);
-        // ---- Verlet::setup: fix adapt, neighbour build, one force evaluation ----
+        {
+            const int *src = reinterpret_cast<const int *>(a.setups + (d.pair_mode == 1 ? 0 : 1 + d.map_id));
+            int *dst = reinterpret_cast<int *>(S.setup);
+            for (int k = tid; k < (int)(sizeof(PairSetup) / 4); k += ESB_THREADS) dst[k] = src[k];
+        }
+        // ---- Verlet::setup: fix adapt, neighbour build, one force evaluation; then n_steps x
+        //      { nve initial; fix adapt; [build]; forces; post_force; nve final } ----
         const long long first = rs.step, last = rs.step + d.n_steps;
         const long long rb = d.ramp_on ? d.ramp_start : first;
         const long long re = d.ramp_on ? d.ramp_stop : last;
@@ -709,25 +743,23 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
         if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
         __syncthreads();
         ESB_TICK(t_obs)
-        build_lists(S, a, r);
-        n_builds++;
-        ESB_TICK(t_build)
-        if (d.pair_mode == 1) force_phase<1, false>(S, a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
-        else force_phase<2, false>(S, a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
-        n_evals++;
-        __syncthreads();
-        ESB_TICK(t_force)
-        n_listed += (unsigned int)S.misc[M_CURLIST];
+        int rebuild = 1;
         for (int it = 0; it <= d.n_steps; it++) {
-            const bool last_pass = (it == d.n_steps);
-            // __syncthreads_or only tells whether ANY thread passed non-zero, so it carries the
-            // rebuild vote; the failure bits travel through shared memory
-            const int rebuild = __syncthreads_or(atom_phase(S, a, it > 0, !last_pass, k0, k1, rs.eval));
+            if (rebuild) { build_lists<NP>(a, r); n_builds++; ESB_TICK(t_build) }
+            if (d.pair_mode == 1) force_phase<NP, 1, false>(a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
+            else force_phase<NP, 2, false>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
+            n_evals++;
+            __syncthreads();
+            ESB_TICK(t_force)
+            n_listed += (unsigned int)S.misc[M_CURLIST];
+            // post_force of this evaluation, final integrate of the step it closes (it > 0) and initial
+            // integrate of the next one (it < n_steps).  __syncthreads_or only tells whether ANY thread
+            // passed non-zero, so it carries the rebuild vote; failure bits travel through shared memory.
+            rebuild = __syncthreads_or(atom_phase<NP>(a, it > 0, it < d.n_steps, k0, k1, rs.eval));
             rs.eval++;
             ESB_TICK(t_atom)
             failed = S.misc[M_FAIL];
-            if (failed) break;
-            if (last_pass) break;
+            if (failed || it == d.n_steps) break;
             rs.step++;
             n_steps_done++;
             if (d.adapt_soft) rs.soft_a = ramp(a.ramp_soft[0], a.ramp_soft[1], rs.step, rb, re);
@@ -735,26 +767,19 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
                 if (d.adapt_bond1) rs.r0[1] = ramp(a.ramp_bond[1][0], a.ramp_bond[1][1], rs.step, rb, re);
                 if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
             }
-            if (rebuild) { build_lists(S, a, r); n_builds++; ESB_TICK(t_build) }
-            if (d.pair_mode == 1) force_phase<1, false>(S, a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
-            else force_phase<2, false>(S, a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
-            n_evals++;
-            __syncthreads();
-            ESB_TICK(t_force)
-            n_listed += (unsigned int)S.misc[M_CURLIST];
         }
         n_pairs += (unsigned int)S.misc[M_PAIRS];
         __syncthreads();
         if (tid == 0) S.misc[M_PAIRS] = 0;
         if (failed) break;
-        if (d.observe) observe(S, a, r, d, rs, delt, sig_nm, c);
+        if (d.observe) observe<NP>(a, r, d, rs, delt, sig_nm, c);
         ESB_TICK(t_obs)
     }
     __syncthreads();
     failed |= S.misc[M_FAIL];
-    for (int k = tid; k < a.n_pad; k += ESB_THREADS) {
-        a.pos4[(size_t)r * a.n_pad + k] = S.pos[k];
-        a.vel4[(size_t)r * a.n_pad + k] = make_float4(S.vx[k], S.vy[k], S.vz[k], 0.0f);
+    for (int k = tid; k < np; k += ESB_THREADS) {
+        a.pos4[(size_t)r * np + k] = S.pos[k];
+        a.vel4[(size_t)r * np + k] = make_float4(S.vx[k], S.vy[k], S.vz[k], 0.0f);
     }
     if (tid == 0) {
         rs.status |= failed;
@@ -771,38 +796,42 @@ esb_run_kernel(const KArgs a, const int chunk_begin, const int n_chunks, const d
 }
 
 // Parity hook: one force evaluation at the stored positions (esb_forces()).
-extern "C" __global__ void __launch_bounds__(ESB_THREADS, 2)
-esb_forces_kernel(const KArgs a, const int pair_mode, const int setup_id, const float soft_a, const int with_post,
+template <int NP>
+__global__ void __launch_bounds__(ESB_THREADS, 2)
+esb_forces_kernel(const __grid_constant__ KArgs a, const int pair_mode, const int setup_id, const float soft_a, const int with_post,
                   const unsigned long long eval, double *f_out, double *e_out)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem S;
-    carve(smem_raw, a, S);
+    const Smem S = carve<NP>(a);
     const int r = blockIdx.x, tid = threadIdx.x;
+    const int np = NP ? NP : a.n_pad;
     const ReplicaScalars rs = a.rs[r];
-    for (int k = tid; k < a.n_pad; k += ESB_THREADS) {
-        S.pos[k] = a.pos4[(size_t)r * a.n_pad + k];
-        const float4 v = a.vel4[(size_t)r * a.n_pad + k];
+    for (int k = tid; k < np; k += ESB_THREADS) {
+        S.pos[k] = a.pos4[(size_t)r * np + k];
+        const float4 v = a.vel4[(size_t)r * np + k];
         S.vx[k] = v.x; S.vy[k] = v.y; S.vz[k] = v.z;
     }
     for (int k = tid; k < a.n_tables * (int)(sizeof(DevTab) / 4); k += ESB_THREADS)
         reinterpret_cast<int *>(S.tab)[k] = reinterpret_cast<const int *>(a.tabs)[k];
     for (int k = tid; k < M_END; k += ESB_THREADS) S.misc[k] = 0;
+    {
+        const int *src = reinterpret_cast<const int *>(a.setups + setup_id);
+        int *dst = reinterpret_cast<int *>(S.setup);
+        for (int k = tid; k < (int)(sizeof(PairSetup) / 4); k += ESB_THREADS) dst[k] = src[k];
+    }
     __syncthreads();
-    load_setup(S, a, setup_id);
-    __syncthreads();
-    build_lists(S, a, r);
+    build_lists<NP>(a, r);
     double en[3] = {0.0, 0.0, 0.0};
-    if (pair_mode == 1) force_phase<1, true>(S, a, r, soft_a, (float)rs.r0[1], (float)rs.r0[2], en);
-    else if (pair_mode == 2) force_phase<2, true>(S, a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], en);
+    if (pair_mode == 1) force_phase<NP, 1, true>(a, r, soft_a, (float)rs.r0[1], (float)rs.r0[2], en);
+    else if (pair_mode == 2) force_phase<NP, 2, true>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], en);
+    else { double eb = 0.0, ea = 0.0; bonded_forces<true>(S, a, (float)rs.r0[1], (float)rs.r0[2], eb, ea); en[1] = eb; en[2] = ea; }
     __syncthreads();
     double e_wall = 0.0;
-    int fail = 0;
     for (int i = tid; i < a.n_atoms; i += ESB_THREADS) {
         float fx = S.fx[i], fy = S.fy[i], fz = S.fz[i];
-        if (with_post)
-            fail |= post_force<true>(a, i, S.pos[i], S.vx[i], S.vy[i], S.vz[i], fx, fy, fz, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), eval, e_wall);
-        if (fail) atomicOr(&S.misc[M_FAIL], fail);
+        if (with_post) {
+            const int fail = post_force<true>(a, i, S.pos[i], S.vx[i], S.vy[i], S.vz[i], fx, fy, fz, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), eval, e_wall);
+            if (fail) atomicOr(&S.misc[M_FAIL], fail);
+        }
         double *o = f_out + ((size_t)r * a.n_atoms + i) * 3;
         o[0] = fx; o[1] = fy; o[2] = fz;
     }
@@ -852,3 +881,44 @@ extern "C" __global__ void esb_unpack_kernel(const float4 *pos4, const float4 *v
 }
 
 size_t esb_smem_bytes(int n_pad, int n_tables) { return smem_bytes_for(n_pad, n_tables); }
+
+// Host launchers: the kernels are instantiated for the bead capacities of the reference's box sizes
+// (box 9..12 without actin: 1050/1172/1290/1400 beads -> 1056/1184/1312/1408; box 11 with actin:
+// 1593 -> 1600) so that all shared-memory array offsets are immediates; any other size runs the
+// generic instantiation.
+#define ESB_FOR_NP(NP_, ...)         \
+    switch (NP_) {                   \
+        case 1056: { constexpr int NPC = 1056; __VA_ARGS__; break; } \
+        case 1184: { constexpr int NPC = 1184; __VA_ARGS__; break; } \
+        case 1312: { constexpr int NPC = 1312; __VA_ARGS__; break; } \
+        case 1408: { constexpr int NPC = 1408; __VA_ARGS__; break; } \
+        case 1600: { constexpr int NPC = 1600; __VA_ARGS__; break; } \
+        default: { constexpr int NPC = 0; __VA_ARGS__; break; }      \
+    }
+
+cudaError_t esb_launch_run(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaSuccess;
+    ESB_FOR_NP(k.n_pad, {
+        e = cudaFuncSetAttribute(esb_run_kernel<NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            esb_run_kernel<NPC><<<k.n_replicas, ESB_THREADS, smem, st>>>(k, chunk_begin, n_chunks, delt, sig_nm);
+            e = cudaGetLastError();
+        }
+    })
+    return e;
+}
+
+cudaError_t esb_launch_forces(const KArgs &k, int pair_mode, int setup_id, float soft_a, int with_post, unsigned long long eval,
+                              double *f_out, double *e_out, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaSuccess;
+    ESB_FOR_NP(k.n_pad, {
+        e = cudaFuncSetAttribute(esb_forces_kernel<NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            esb_forces_kernel<NPC><<<k.n_replicas, ESB_THREADS, smem, st>>>(k, pair_mode, setup_id, soft_a, with_post, eval, f_out, e_out);
+            e = cudaGetLastError();
+        }
+    })
+    return e;
+}
