@@ -110,6 +110,8 @@ struct esb_handle {
     double *d_frames = nullptr;
     unsigned short *d_hist = nullptr;
     unsigned long long *d_counters = nullptr;
+    int *d_sched = nullptr;
+    int n_sm = 148;
     Layout lay = {0, 0, 0, 0};
     std::vector<ReplicaScalars> rs_host;
     int ncx = 1, ncy = 1, ncz = 1;
@@ -307,6 +309,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     if (rc) return rc;
     CK(cudaSetDevice(device));
     esb_handle *h = new esb_handle();
+    { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, device) == cudaSuccess) h->n_sm = p.multiProcessorCount; }
     h->device = device; h->R = n_replicas; h->N = n_atoms; h->n_types = n_types;
     h->n_pad = (n_atoms + 31) & ~31;
     if (const char *s = getenv("ESB_SKIN")) h->skin = atof(s);
@@ -321,8 +324,8 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     }
     const size_t tot = (size_t)n_replicas * h->n_pad;
     if ((rc = dev_alloc(&h->d_pos4, tot)) || (rc = dev_alloc(&h->d_vel4, tot)) || (rc = dev_alloc(&h->d_rs, (size_t)n_replicas)) ||
-        (rc = dev_alloc(&h->d_frozen, (size_t)h->n_pad)) || (rc = dev_alloc(&h->d_nl_pool, (size_t)n_replicas * ESB_NL_POOL)) ||
-        (rc = dev_alloc(&h->d_nl_qinfo, 2 * tot)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * ESB_N_COUNTERS))) {
+        (rc = dev_alloc(&h->d_frozen, (size_t)h->n_pad)) || (rc = dev_alloc(&h->d_nl_pool, (size_t)n_replicas * h->n_pad * ESB_NL_STRIDE + 256)) ||
+        (rc = dev_alloc(&h->d_nl_qinfo, 2 * tot)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * ESB_N_COUNTERS)) || (rc = dev_alloc(&h->d_sched, (size_t)n_replicas + 1))) {
         esb_destroy(h);
         return rc;
     }
@@ -349,7 +352,7 @@ int esb_destroy(esb_handle *h)
     cudaFree(h->d_spec); cudaFree(h->d_setups); cudaFree(h->d_tabs_closed); cudaFree(h->d_tabs_array);
     cudaFree(h->d_tabval); cudaFree(h->d_tabe); cudaFree(h->d_nl_pool); cudaFree(h->d_nl_qinfo); cudaFree(h->d_descs);
     cudaFree(h->d_enh); cudaFree(h->d_s5p); cudaFree(h->d_cluster_r); cudaFree(h->d_frames); cudaFree(h->d_hist);
-    cudaFree(h->d_counters);
+    cudaFree(h->d_counters); cudaFree(h->d_sched);
     delete h;
     return ESB_OK;
 }
@@ -719,7 +722,7 @@ int esb_run(esb_handle *h, int chunk_begin, int n_chunks, void *stream)
     if (rc) return rc;
     KArgs k;
     fill_kargs(h, k, false);
-    CK(esb_launch_run(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem, (cudaStream_t)stream));
+    CK(esb_launch_run(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem, (cudaStream_t)stream, h->d_sched, h->n_sm));
     return ESB_OK;
 }
 

@@ -14,9 +14,8 @@
 #define ESB_GROUPS (ESB_THREADS / ESB_G)
 #define ESB_MAX_TERMS 8              // bonded terms per atom (linear chain: 2 bonds + 3 angles)
 #define ESB_MAX_SPEC 8               // excluded partners per atom (linear chain: 6)
-#define ESB_NL_CHUNK 2048            // arena chunk a lane-group grabs
 #define ESB_NL_MAXNB 1023            // neighbours per atom (12-bit count in the head word)
-#define ESB_NL_POOL (256 * 1024)     // u16 entries per replica arena
+#define ESB_NL_STRIDE 1024           // list arena per bead (entries); LAMMPS: neigh_modify one 10000
 #define ESB_NCLASS 5                 // species classes for the slot sort: chromatin-like, actin, RBP, RNP, Ser5P
 #define ESB_N_COUNTERS 10             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases
 #define ESB_N_SETUPS 9               // 0 = pair soft, 1..4 = table maps 0..3 (closed form + patch), 5..8 = same maps, array lookups
@@ -90,7 +89,7 @@ struct KArgs {
     const float *tabval;      // patch / array values (F/r), fp32
     const float *tabe;        // energy arrays (hook)
     int tlm1;
-    unsigned int *nl_pool;    // [R][ESB_NL_POOL]  neighbour index | table id << 16
+    unsigned int *nl_pool;    // [R][n_pad][ESB_NL_STRIDE]  neighbour index | table id << 16
     uint2 *nl_qinfo;          // [R][2][n_pad] {list start, atom | count << 16}: [0] sorted by list length (force order), [1] slot order (build)
     unsigned char class_of[ESB_MAXT + 4];
     const esb_chunk_desc *descs;
@@ -123,6 +122,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 __device__ __forceinline__ float u32_centered(uint32_t u) { return (float)(int32_t)u * 0x1p-32f; }
 
 size_t esb_smem_bytes(int n_pad, int n_tables);
-cudaError_t esb_launch_run(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st);
+cudaError_t esb_launch_run(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
+                           int *sched, int n_sm);
 cudaError_t esb_launch_forces(const KArgs &k, int pair_mode, int setup_id, float soft_a, int with_post, unsigned long long eval,
                               double *f_out, double *e_out, size_t smem, cudaStream_t st);

@@ -73,6 +73,24 @@ __device__ __forceinline__ Smem carve(const KArgs &a)
     return S;
 }
 
+// MUFU.RCP without the denormal wrapper that __fdividef(1, x) drags in (x is O(0.3 .. 1e3) here)
+__device__ __forceinline__ float rcp_approx(const float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Shared memory viewed as float4 words: indexing this array (instead of dereferencing pointers
+// carried in a struct) lets the compiler emit LDS [reg + immediate] in the hot loops.
+extern __shared__ __align__(16) float4 smem4[];
+template <int NP>
+__device__ __forceinline__ int tab_off4(const KArgs &a)
+{
+    const int np = NP ? NP : a.n_pad;
+    return (np * 52 + (int)((sizeof(PairSetup) + 15) & ~(size_t)15)) / 16;   // float4 index of S.tab
+}
+
 __device__ __forceinline__ int cell_coord(float x, float lo, float inv, int n)
 {
     int c = (int)((x - lo) * inv);
@@ -109,7 +127,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
     unsigned int *cw = reinterpret_cast<unsigned int *>(S.cend);
     const int ncw = (nslots + 2 + 1) >> 1;
     for (int w = tid; w < ncw; w += ESB_THREADS) cw[w] = 0u;
-    if (tid == 0) { S.misc[M_POOLCUR] = 0; S.misc[M_CURLIST] = 0; }
+    if (tid == 0) S.misc[M_CURLIST] = 0;
     __syncthreads();
     // count (slot s is stored at position s+1 so that, after the scan, position s holds start(s))
     for (int i = tid; i < n; i += ESB_THREADS) {
@@ -158,92 +176,82 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
     }
     __syncthreads();
 
+    // ---- candidate tests: one quad (4 consecutive beads of the slot order: same cell and class, hence
+    // the same candidate rows) per warp; every lane takes one candidate j and tests it against all
+    // four beads, so a warp iteration performs 128 distance tests for two shared-memory loads.
+    // Accepted (bead, j) pairs are compacted per bead with a ballot; bead i owns the fixed arena
+    // [i * ESB_NL_STRIDE, (i+1) * ESB_NL_STRIDE) of the replica's pool.
     const unsigned int FULL = 0xffffffffu;
-    const int gl = lane & (ESB_G - 1), grp = lane / ESB_G;
-    const int gshift = grp * ESB_G;
-    unsigned int *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESB_NL_STRIDE;
     uint2 *qbuild = a.nl_qinfo + ((size_t)r * 2 + 1) * a.n_pad;     // descriptors in build (slot) order
     const float lox = a.lo[0], loy = a.lo[1], loz = a.lo[2], cinv = a.cell_inv;
     const int ncx = a.ncx, ncy = a.ncy, ncz = a.ncz, n_topo = a.n_topo;
-    int cursor = 0, limit = 0;
     unsigned int listed = 0;
     const int nquads = (n + 3) >> 2;
     for (int q = warp; q < nquads; q += ESB_THREADS / 32) {
-        const int idx = 4 * q + grp;
-        bool valid = idx < n;
-        const int i = valid ? S.sidx[idx] : 0;
-        const bool need = valid && (limit - cursor < ESB_NL_MAXNB + 1);
-        int c = 0;
-        if (need && gl == 0) c = atomicAdd(&S.misc[M_POOLCUR], ESB_NL_CHUNK);
-        c = __shfl_sync(FULL, c, gshift);
-        if (need) {
-            if (c + ESB_NL_CHUNK > ESB_NL_POOL) {
-                if (gl == 0) atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH);
-                valid = false;
-            } else { cursor = c; limit = c + ESB_NL_CHUNK; }
+        int ia[4], ta[4], cnt[4];
+        float4 pa[4];
+        int x0 = ncx, x1 = -1, y0 = ncy, y1 = -1, z0 = ncz, z1 = -1;
+        bool any_topo = false;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int idx = min(4 * q + b, n - 1);               // the last quad may repeat its last bead
+            ia[b] = S.sidx[idx];
+            pa[b] = S.pos[ia[b]];
+            ta[b] = __float_as_int(pa[b].w) & 0xff;
+            cnt[b] = 0;
+            const int rng = S.setup->range[ta[b]];
+            const int cx = cell_coord(pa[b].x, lox, cinv, ncx), cy = cell_coord(pa[b].y, loy, cinv, ncy), cz = cell_coord(pa[b].z, loz, cinv, ncz);
+            x0 = min(x0, max(cx - rng, 0)); x1 = max(x1, min(cx + rng, ncx - 1));
+            y0 = min(y0, max(cy - rng, 0)); y1 = max(y1, min(cy + rng, ncy - 1));
+            z0 = min(z0, max(cz - rng, 0)); z1 = max(z1, min(cz + rng, ncz - 1));
+            any_topo |= ia[b] < n_topo;
         }
-        const float4 pi = S.pos[i];
-        const int ti = __float_as_int(pi.w) & 0xff;
-        const int rng = S.setup->range[ti];
-        const int cx = cell_coord(pi.x, lox, cinv, ncx);
-        const int cy = cell_coord(pi.y, loy, cinv, ncy);
-        const int cz = cell_coord(pi.z, loz, cinv, ncz);
-        const int x0 = max(cx - rng, 0), x1 = min(cx + rng, ncx - 1);
-        const int y0 = max(cy - rng, 0), y1 = min(cy + rng, ncy - 1);
-        const int z0 = max(cz - rng, 0), z1 = min(cz + rng, ncz - 1);
-        const int nrows = valid ? (y1 - y0 + 1) * (z1 - z0 + 1) : 0;
-        const int rows_max = __reduce_max_sync(FULL, nrows);
-        const bool topo_i = i < n_topo;
-        uint4 sp = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        if (topo_i) sp = *reinterpret_cast<const uint4 *>(a.spec + (size_t)i * ESB_MAX_SPEC);
-        const float *cs = S.setup->cutsq_skin + ti * ESB_MAXT;
-        const unsigned char *tabid = S.setup->tabid + ti * ESB_MAXT;
-        unsigned int *out = pool + cursor;
-        int cnt = 0;
-        int yy = y0, zz = z0;
-        for (int row_i = 0; row_i < rows_max; row_i++) {
-            int ka = 0, kb = 0;
-            if (row_i < nrows) {
+        for (int zz = z0; zz <= z1; zz++)
+            for (int yy = y0; yy <= y1; yy++) {
                 const int row = (zz * ncy + yy) * ncx;
                 const int s_first = (row + x0) * ESB_NCLASS;
-                ka = s_first ? S.cend[s_first - 1] : 0;
-                kb = S.cend[(row + x1) * ESB_NCLASS + ESB_NCLASS - 1];
-                if (++yy > y1) { yy = y0; zz++; }
-            }
-            const int len_max = __reduce_max_sync(FULL, kb - ka);
-            for (int k0 = 0; k0 < len_max; k0 += ESB_G) {
-                const int k = ka + k0 + gl;
-                bool ok = false;
-                unsigned int ent = 0u;
-                if (k < kb) {
-                    const int j = S.sidx[k];
+                const int ka = s_first ? S.cend[s_first - 1] : 0;
+                const int kb = S.cend[(row + x1) * ESB_NCLASS + ESB_NCLASS - 1];
+                for (int k0 = ka; k0 < kb; k0 += 32) {
+                    const int k = k0 + lane;
+                    const bool live = k < kb;
+                    const int j = live ? S.sidx[k] : 0;
                     const float4 pj = S.pos[j];
-                    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                    const float r2 = dx * dx + dy * dy + dz * dz;
                     const int tj = __float_as_int(pj.w) & 0xff;
-                    ok = (r2 < cs[tj]) && (j != i);
-                    ent = (unsigned int)j | ((unsigned int)tabid[tj] << 16);
-                    if (ok && topo_i && j < n_topo) {
-                        const unsigned int jj = (unsigned int)j;
-                        ok = !((sp.x & 0xffffu) == jj || (sp.x >> 16) == jj || (sp.y & 0xffffu) == jj || (sp.y >> 16) == jj ||
-                               (sp.z & 0xffffu) == jj || (sp.z >> 16) == jj || (sp.w & 0xffffu) == jj || (sp.w >> 16) == jj);
+                    const bool topo_j = any_topo && j < n_topo;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const float dx = pa[b].x - pj.x, dy = pa[b].y - pj.y, dz = pa[b].z - pj.z;
+                        const float r2 = dx * dx + dy * dy + dz * dz;
+                        bool ok = live && (r2 < S.setup->cutsq_skin[ta[b] * ESB_MAXT + tj]) && (j != ia[b]);
+                        if (ok && topo_j && ia[b] < n_topo) {
+                            const uint4 sp = *reinterpret_cast<const uint4 *>(a.spec + (size_t)ia[b] * ESB_MAX_SPEC);
+                            const unsigned int jj = (unsigned int)j;
+                            ok = !((sp.x & 0xffffu) == jj || (sp.x >> 16) == jj || (sp.y & 0xffffu) == jj || (sp.y >> 16) == jj ||
+                                   (sp.z & 0xffffu) == jj || (sp.z >> 16) == jj || (sp.w & 0xffffu) == jj || (sp.w >> 16) == jj);
+                        }
+                        const unsigned int bits = __ballot_sync(FULL, ok);
+                        if (ok) {
+                            const int slot = cnt[b] + __popc(bits & lt_mask);
+                            if (slot < ESB_NL_MAXNB)
+                                pool[(size_t)ia[b] * ESB_NL_STRIDE + slot] = (unsigned int)j | ((unsigned int)S.setup->tabid[ta[b] * ESB_MAXT + tj] << 16);
+                        }
+                        cnt[b] += __popc(bits);
                     }
                 }
-                const unsigned int bits = (__ballot_sync(FULL, ok) >> gshift) & ((1u << ESB_G) - 1u);
-                if (ok) {
-                    const int slot = cnt + __popc(bits & ((1u << gl) - 1u));
-                    if (slot < ESB_NL_MAXNB) out[slot] = ent;
-                }
-                cnt += __popc(bits);
+            }
+        if (lane < 4) {
+            const int idx = 4 * q + lane;
+            int c = lane == 0 ? cnt[0] : lane == 1 ? cnt[1] : lane == 2 ? cnt[2] : cnt[3];
+            const int i = lane == 0 ? ia[0] : lane == 1 ? ia[1] : lane == 2 ? ia[2] : ia[3];
+            if (idx < n) {
+                if (c > ESB_NL_MAXNB) { atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH); c = ESB_NL_MAXNB; }
+                qbuild[idx] = make_uint2((unsigned int)i * ESB_NL_STRIDE, (unsigned int)i | ((unsigned int)c << 16));
+                listed += c;
             }
         }
-        if (cnt > ESB_NL_MAXNB) {
-            if (gl == 0) atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH);
-            cnt = ESB_NL_MAXNB;
-        }
-        if (!valid) cnt = 0;
-        if (idx < a.n_pad && gl == 0) { qbuild[idx] = make_uint2((unsigned int)cursor, (unsigned int)i | ((unsigned int)cnt << 16)); listed += cnt; }
-        cursor += cnt;
     }
     if (listed) atomicAdd(&S.misc[M_CURLIST], (int)listed);
     __syncthreads();
@@ -368,9 +376,9 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
     double e_pair = 0.0, e_bond = 0.0, e_angle = 0.0;
     bonded_forces<ENERGY>(S, a, r0_1, r0_2, e_bond, e_angle);
     __syncthreads();
-    const unsigned int *pool = a.nl_pool + (size_t)r * ESB_NL_POOL;
+    const unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESB_NL_STRIDE;
     const uint2 *qinfo = a.nl_qinfo + (size_t)r * 2 * a.n_pad;
-    const unsigned char *tabbase = reinterpret_cast<const unsigned char *>(S.tab);
+    const int toff4 = tab_off4<NP>(a);
     const float *tabval = a.tabval;
     const int tlm1 = a.tlm1;
     unsigned int npairs = 0;
@@ -384,20 +392,22 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
         const uint2 qi = qi_next;
         const int qn = q + ESB_THREADS / 32;
         qi_next = make_uint2(0u, 0u);
-        if (qn < nquads && 4 * qn + grp < n) qi_next = qinfo[4 * qn + grp];
+        if (qn < nquads && 4 * qn + grp < n) qi_next = __ldcg(&qinfo[4 * qn + grp]);
         const bool valid = 4 * q + grp < n;
         const int i = (int)(qi.y & 0xffffu);
         const int cnt = valid ? (int)(qi.y >> 16) : 0;
         const unsigned int *nl = pool + qi.x;
-        const float4 pi = S.pos[i];
+        const float4 pi = smem4[i];
         const int cnt_max = __reduce_max_sync(FULL, cnt);
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
         // The list lives in L2/HBM: four loads per lane are kept in flight (entries e, e+G, e+2G, e+3G)
         // so that their latency overlaps the arithmetic of the entries before them.
-        auto ld = [&](int k) -> unsigned int { return (k < cnt) ? nl[k] : 0u; };
+        // Loads past the end of a list are harmless (every bead owns a fixed arena and the pool is padded),
+        // so the prefetches carry no predicate; only the use of an entry is guarded.
+        const unsigned int *lp = nl + gl;
         auto pair_body = [&](const unsigned int ent, const int e) {
             if (e < cnt) {
-                const float4 pj = S.pos[ent & 0xffffu];
+                const float4 pj = smem4[ent & 0xffffu];
                 const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 const float r2 = dx * dx + dy * dy + dz * dz;
                 float fpair;
@@ -413,17 +423,18 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                     npairs++;
                 } else {
                     const unsigned int tb = ent >> 16;                          // table id of the pair (fixed between builds)
-                    const unsigned char *T = tabbase + tb * (unsigned int)sizeof(DevTab);
-                    const float4 t0 = *reinterpret_cast<const float4 *>(T);          // cutsq, invdelta_f, delta, innersq_f
+                    const int T4 = toff4 + 3 * (int)tb;                               // DevTab = 3 float4 words
+                    const float4 t0 = smem4[T4];                                      // cutsq, invdelta_f, delta, innersq_f
                     if (!(r2 < t0.x)) return;
-                    const float4 t1 = *reinterpret_cast<const float4 *>(T + 16);     // K, is6, c, patch
+                    const float4 t1 = smem4[T4 + 1];                                  // K, is6, c, patch
                     const float u = (r2 - t0.w) * t0.y;
                     int it = (int)u;
                     const float frac = u - (float)it;
                     // |u - u_exact| <= 8 ulp-relative (dx: 1, squares+sums: 5, offset+scale: 2) = 4.8e-7 u
                     const float margin = fmaf(u, 5.0e-7f, 1.0e-4f);
                     if (!(frac > margin && frac < 1.0f - margin)) {
-                        const double innersq = *reinterpret_cast<const double *>(T + 32), invdelta = *reinterpret_cast<const double *>(T + 40);
+                        const double2 t2 = *reinterpret_cast<const double2 *>(&smem4[T4 + 2]);
+                        const double innersq = t2.x, invdelta = t2.y;
                         const double ddx = __dsub_rn((double)pi.x, (double)pj.x), ddy = __dsub_rn((double)pi.y, (double)pj.y),
                                      ddz = __dsub_rn((double)pi.z, (double)pj.z);
                         const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
@@ -436,7 +447,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                     const float qm = fmaf((float)it + 0.5f, t0.z, t0.w);
                     const float q2 = qm * qm;
                     const float x = fmaf(q2 * qm, t1.y, t1.z);
-                    float inv = __fdividef(1.0f, x);
+                    float inv = rcp_approx(x);
                     inv = inv * fmaf(-x, inv, 2.0f);
                     fpair = t1.x * q2 * (2.0f - x) * (inv * inv * inv);
                     if (!closed) fpair = tabval[tb * (unsigned int)tlm1 + it];   // predicated load: patch bins are rare
@@ -446,15 +457,16 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                 fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
             }
         };
-        unsigned int w0 = ld(gl), w1 = ld(gl + ESB_G), w2 = ld(gl + 2 * ESB_G), w3 = ld(gl + 3 * ESB_G);
+        unsigned int w0 = __ldcg(lp), w1 = __ldcg(lp + ESB_G), w2 = __ldcg(lp + 2 * ESB_G), w3 = __ldcg(lp + 3 * ESB_G);
         for (int e0 = 0; e0 < cnt_max; e0 += 4 * ESB_G) {
             const int e = e0 + gl;
+            lp += 4 * ESB_G;
             const unsigned int c0 = w0, c1 = w1;
-            w0 = ld(e + 4 * ESB_G); w1 = ld(e + 5 * ESB_G);
+            w0 = __ldcg(lp); w1 = __ldcg(lp + ESB_G);
             pair_body(c0, e); pair_body(c1, e + ESB_G);
             if (e0 + 2 * ESB_G >= cnt_max) break;
             const unsigned int c2 = w2, c3 = w3;
-            w2 = ld(e + 6 * ESB_G); w3 = ld(e + 7 * ESB_G);
+            w2 = __ldcg(lp + 2 * ESB_G); w3 = __ldcg(lp + 3 * ESB_G);
             pair_body(c2, e + 2 * ESB_G); pair_body(c3, e + 3 * ESB_G);
         }
 #pragma unroll
@@ -701,33 +713,61 @@ __device__ __noinline__ void observe(const KArgs &a, int r, const esb_chunk_desc
 }  // namespace
 
 // ================================================================================================
+// One persistent CTA per SM slot.  Work items are (replica, chunk) pairs handed out in chunk-major
+// order from a global ticket counter; item (r, c) may start as soon as (r, c-1) is finished, which
+// its producer publishes in progress[r].  With more replicas than resident CTAs the replicas thus
+// advance in a ring and no SM idles while another still has a queue (a plain grid of R CTAs would
+// leave 148*3 - (R mod 148*3) slots empty for the whole last wave).  The grid never exceeds the
+// number of co-resident CTAs, so a waiting CTA's producer is always running.
 template <int NP>
 __global__ void __launch_bounds__(ESB_THREADS, 3)
-esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int n_chunks, const double delt, const double sig_nm)
+esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int n_chunks, const double delt, const double sig_nm,
+               int *ticket, int *progress)
 {
     const Smem S = carve<NP>(a);
-    const int r = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const int np = NP ? NP : a.n_pad;
-    ReplicaScalars rs = a.rs[r];
-    if (rs.status != 0) return;   // a failed replica no longer advances (LAMMPS would have aborted)
-
-    for (int k = tid; k < np; k += ESB_THREADS) {
-        S.pos[k] = a.pos4[(size_t)r * np + k];
-        const float4 v = a.vel4[(size_t)r * np + k];
-        S.vx[k] = v.x; S.vy[k] = v.y; S.vz[k] = v.z;
-    }
     for (int k = tid; k < a.n_tables * (int)(sizeof(DevTab) / 4); k += ESB_THREADS)
         reinterpret_cast<int *>(S.tab)[k] = reinterpret_cast<const int *>(a.tabs)[k];
-    for (int k = tid; k < M_END; k += ESB_THREADS) S.misc[k] = 0;
-    const uint32_t k0 = (uint32_t)rs.seed, k1 = (uint32_t)(rs.seed >> 32);
-    unsigned long long n_evals = 0, n_builds = 0, n_steps_done = 0, n_pairs = 0, n_listed = 0;
-    long long t_atom = 0, t_build = 0, t_force = 0, t_obs = 0, t_mark = clock64();
-#define ESB_TICK(acc) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; }
-    int failed = 0;
+    __shared__ int s_item;
+    const int n_items = a.n_replicas * n_chunks;
 
-    for (int c = chunk_begin; c < chunk_begin + n_chunks && !failed; c++) {
-        const esb_chunk_desc d = a.descs[c];
+    for (;;) {
         __syncthreads();
+        if (tid == 0) s_item = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) break;
+        const int r = item % a.n_replicas, lc = item / a.n_replicas;       // local chunk index within this launch
+        const int c = chunk_begin + lc;
+        if (tid == 0) {
+            while (atomicAdd(&progress[r], 0) < lc) __nanosleep(256);
+            __threadfence();
+        }
+        __syncthreads();
+        ReplicaScalars rs;
+        {
+            const volatile int *src = reinterpret_cast<const volatile int *>(&a.rs[r]);
+            int *dst = reinterpret_cast<int *>(&rs);
+            for (int k = 0; k < (int)(sizeof(ReplicaScalars) / 4); k++) dst[k] = src[k];
+        }
+        if (rs.status != 0) {                                                // a failed replica no longer advances
+            __syncthreads();
+            if (tid == 0) { __threadfence(); atomicExch(&progress[r], lc + 1); }
+            continue;
+        }
+        for (int k = tid; k < np; k += ESB_THREADS) {
+            S.pos[k] = __ldcg(&a.pos4[(size_t)r * np + k]);                 // written by another SM one chunk ago: bypass L1
+            const float4 v = __ldcg(&a.vel4[(size_t)r * np + k]);
+            S.vx[k] = v.x; S.vy[k] = v.y; S.vz[k] = v.z;
+        }
+        for (int k = tid; k < M_END; k += ESB_THREADS) S.misc[k] = 0;
+        const uint32_t k0 = (uint32_t)rs.seed, k1 = (uint32_t)(rs.seed >> 32);
+        unsigned long long n_evals = 0, n_builds = 0, n_steps_done = 0, n_listed = 0;
+        long long t_atom = 0, t_build = 0, t_force = 0, t_obs = 0, t_mark = clock64();
+#define ESB_TICK(acc) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; }
+        int failed = 0;
+        const esb_chunk_desc d = a.descs[c];
         {
             const int *src = reinterpret_cast<const int *>(a.setups + (d.pair_mode == 1 ? 0 : 1 + d.map_id));
             int *dst = reinterpret_cast<int *>(S.setup);
@@ -768,30 +808,29 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
                 if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
             }
         }
-        n_pairs += (unsigned int)S.misc[M_PAIRS];
-        __syncthreads();
-        if (tid == 0) S.misc[M_PAIRS] = 0;
-        if (failed) break;
-        if (d.observe) observe<NP>(a, r, d, rs, delt, sig_nm, c);
+        const unsigned long long n_pairs = (unsigned int)S.misc[M_PAIRS];
+        if (!failed && d.observe) observe<NP>(a, r, d, rs, delt, sig_nm, c);
         ESB_TICK(t_obs)
-    }
-    __syncthreads();
-    failed |= S.misc[M_FAIL];
-    for (int k = tid; k < np; k += ESB_THREADS) {
-        a.pos4[(size_t)r * np + k] = S.pos[k];
-        a.vel4[(size_t)r * np + k] = make_float4(S.vx[k], S.vy[k], S.vz[k], 0.0f);
-    }
-    if (tid == 0) {
-        rs.status |= failed;
-        a.rs[r] = rs;
-        unsigned long long *cn = a.counters + (size_t)r * ESB_N_COUNTERS;
-        cn[6] += (unsigned long long)t_atom; cn[7] += (unsigned long long)t_build;
-        cn[8] += (unsigned long long)t_force; cn[9] += (unsigned long long)t_obs;
-        cn[0] += n_evals; cn[1] += n_builds;
-        cn[2] += n_pairs;
-        cn[3] += n_listed;
-        cn[4] += n_steps_done;
-        cn[5] = (unsigned long long)rs.total_active;
+        __syncthreads();
+        failed |= S.misc[M_FAIL];
+        for (int k = tid; k < np; k += ESB_THREADS) {
+            a.pos4[(size_t)r * np + k] = S.pos[k];
+            a.vel4[(size_t)r * np + k] = make_float4(S.vx[k], S.vy[k], S.vz[k], 0.0f);
+        }
+        if (tid == 0) {
+            rs.status |= failed;
+            a.rs[r] = rs;
+            unsigned long long *cn = a.counters + (size_t)r * ESB_N_COUNTERS;
+            cn[6] += (unsigned long long)t_atom; cn[7] += (unsigned long long)t_build;
+            cn[8] += (unsigned long long)t_force; cn[9] += (unsigned long long)t_obs;
+            cn[0] += n_evals; cn[1] += n_builds;
+            cn[2] += n_pairs;
+            cn[3] += n_listed;
+            cn[4] += n_steps_done;
+            cn[5] = (unsigned long long)rs.total_active;
+        }
+        __syncthreads();                         // every thread's state stores are issued ...
+        if (tid == 0) { __threadfence(); atomicExch(&progress[r], lc + 1); }   // ... and published
     }
 }
 
@@ -896,13 +935,19 @@ size_t esb_smem_bytes(int n_pad, int n_tables) { return smem_bytes_for(n_pad, n_
         default: { constexpr int NPC = 0; __VA_ARGS__; break; }      \
     }
 
-cudaError_t esb_launch_run(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st)
+cudaError_t esb_launch_run(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
+                           int *sched /* [1 + n_replicas] device ints: ticket, progress[] */, int n_sm)
 {
     cudaError_t e = cudaSuccess;
     ESB_FOR_NP(k.n_pad, {
         e = cudaFuncSetAttribute(esb_run_kernel<NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per_sm = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, esb_run_kernel<NPC>, ESB_THREADS, smem);
+        if (e == cudaSuccess && per_sm < 1) e = cudaErrorLaunchOutOfResources;
+        if (e == cudaSuccess) e = cudaMemsetAsync(sched, 0, sizeof(int) * (size_t)(1 + k.n_replicas), st);
         if (e == cudaSuccess) {
-            esb_run_kernel<NPC><<<k.n_replicas, ESB_THREADS, smem, st>>>(k, chunk_begin, n_chunks, delt, sig_nm);
+            const int grid = k.n_replicas < per_sm * n_sm ? k.n_replicas : per_sm * n_sm;   // all CTAs co-resident
+            esb_run_kernel<NPC><<<grid, ESB_THREADS, smem, st>>>(k, chunk_begin, n_chunks, delt, sig_nm, sched, sched + 1);
             e = cudaGetLastError();
         }
     })
