@@ -273,7 +273,8 @@ def run_native(args, w):
                     "d2h_bytes_per_step": int(2 * R * n_pad * 16 + R * 72), "ms_per_step": ms_e2e / K},
             "gpu_launches": 1,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": None if not prof else prof.get("dram_bytes_per_launch"),
+                         "traffic": None if not prof else prof.get("dram_bytes_per_step", 0) * K * (R / max(prof.get("replicas", R), 1)),
+                         "traffic_source": None if not prof else prof.get("source"),
                          "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({which} MEASURED_PEAKS.json); MEASURED_PEAKS has no FP32 entry",
                          "kernel": "esb_run_kernel", "launch_ms": ms, "steps_per_launch": K, "flop_per_replica_step": fl,
                          "pairs_in_cut_per_step": pairs_in_cut, "pairs_listed_per_step": listed,
