@@ -107,7 +107,7 @@ struct esb_handle {
     esb_chunk_desc *d_descs = nullptr;
     int *d_enh = nullptr, *d_s5p = nullptr;
     double *d_cluster_r = nullptr;
-    double *d_frames = nullptr;
+    double *d_frames = nullptr, *d_rawd = nullptr;
     unsigned short *d_hist = nullptr;
     unsigned long long *d_counters = nullptr;
     int *d_sched = nullptr;
@@ -276,7 +276,7 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     }
     k.descs = h->d_descs;
     k.lay = h->lay; k.enh_idx = h->d_enh; k.s5p_idx = h->d_s5p; k.cluster_r = h->d_cluster_r;
-    k.frames = h->d_frames; k.hist = h->d_hist; k.max_chunks = h->n_chunks;
+    k.frames = h->d_frames; k.rawd = h->d_rawd; k.hist = h->d_hist; k.max_chunks = h->n_chunks;
     k.counters = h->d_counters;
     return ESB_OK;
 }
@@ -351,7 +351,7 @@ int esb_destroy(esb_handle *h)
     cudaFree(h->d_pos4); cudaFree(h->d_vel4); cudaFree(h->d_rs); cudaFree(h->d_frozen); cudaFree(h->d_bterm);
     cudaFree(h->d_spec); cudaFree(h->d_setups); cudaFree(h->d_tabs_closed); cudaFree(h->d_tabs_array);
     cudaFree(h->d_tabval); cudaFree(h->d_tabe); cudaFree(h->d_nl_pool); cudaFree(h->d_nl_qinfo); cudaFree(h->d_descs);
-    cudaFree(h->d_enh); cudaFree(h->d_s5p); cudaFree(h->d_cluster_r); cudaFree(h->d_frames); cudaFree(h->d_hist);
+    cudaFree(h->d_enh); cudaFree(h->d_s5p); cudaFree(h->d_cluster_r); cudaFree(h->d_frames); cudaFree(h->d_rawd); cudaFree(h->d_hist);
     cudaFree(h->d_counters); cudaFree(h->d_sched);
     delete h;
     return ESB_OK;
@@ -690,6 +690,8 @@ int esb_set_schedule(esb_handle *h, int n_chunks, const esb_chunk_desc *descs)
     if (n_chunks != h->n_chunks || !h->d_frames) {
         if ((rc = dev_alloc(&h->d_frames, (size_t)h->R * n_chunks * ESB_FRAME_DOUBLES))) return rc;
         if ((rc = dev_alloc(&h->d_hist, (size_t)h->R * n_chunks * (ESB_N_SHELL - 1)))) return rc;
+        if ((rc = dev_alloc(&h->d_rawd, (size_t)h->R * n_chunks * 2))) return rc;
+        CK(cudaMemset(h->d_rawd, 0, (size_t)h->R * n_chunks * 2 * sizeof(double)));
         CK(cudaMemset(h->d_frames, 0, (size_t)h->R * n_chunks * ESB_FRAME_DOUBLES * sizeof(double)));
         CK(cudaMemset(h->d_hist, 0, (size_t)h->R * n_chunks * (ESB_N_SHELL - 1) * sizeof(unsigned short)));
     }
@@ -773,6 +775,16 @@ int esb_get_frames(esb_handle *h, int chunk_begin, int n_chunks, double *out, in
                         (size_t)n_chunks * nb * 2, h->R, cudaMemcpyDeviceToHost));
         for (size_t q = 0; q < tmp.size(); q++) hist[q] = tmp[q];
     }
+    return ESB_OK;
+}
+
+int esb_get_raw_distances(esb_handle *h, int chunk_begin, int n_chunks, double *out)
+{
+    if (!h || !out) return fail(ESB_EINVAL, "NULL argument");
+    if (chunk_begin < 0 || n_chunks < 1 || chunk_begin + n_chunks > h->n_chunks) return fail(ESB_EINVAL, "chunk range outside the schedule");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy2D(out, (size_t)n_chunks * 2 * sizeof(double), h->d_rawd + (size_t)chunk_begin * 2, (size_t)h->n_chunks * 2 * sizeof(double),
+                    (size_t)n_chunks * 2 * sizeof(double), h->R, cudaMemcpyDeviceToHost));
     return ESB_OK;
 }
 

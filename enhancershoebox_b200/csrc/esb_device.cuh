@@ -98,6 +98,7 @@ struct KArgs {
     const int *enh_idx, *s5p_idx;
     const double *cluster_r;  // [50]
     double *frames;           // [R][max_chunks][9]
+    double *rawd;             // [R][max_chunks][2]  d_rp, d_rg in bead units (gene_stats.txt needs d_rg < 3 exactly)
     unsigned short *hist;     // [R][max_chunks][49]
     int max_chunks;
     unsigned long long *counters;  // [R][ESB_N_COUNTERS]

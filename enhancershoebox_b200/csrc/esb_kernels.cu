@@ -701,6 +701,8 @@ __device__ __noinline__ void observe(const KArgs &a, int r, const esb_chunk_desc
             f[6] = (double)n_prom;
             f[7] = (double)n_gene;
             f[8] = (double)rs.gene_state;
+            a.rawd[((size_t)r * a.max_chunks + slot) * 2] = d_rp;
+            a.rawd[((size_t)r * a.max_chunks + slot) * 2 + 1] = d_rg;
         }
     }
     if (slot < a.max_chunks && a.hist)

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "esb_sync": (C.c_int, [C.c_void_p]),
     "esb_forces": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "esb_get_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "esb_get_raw_distances": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "esb_get_frames_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "esb_get_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "esb_get_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
@@ -314,6 +315,13 @@ class ShoeboxBatch:
         hist = np.empty((self.R, n, N_SHELL - 1), np.int32) if with_hist else None
         self._check(self.lib.esb_get_frames(self.h, chunk_begin, n, _dp(out), None if hist is None else _ip(hist)))
         return (out, hist) if with_hist else out
+
+    def raw_distances(self, chunk_begin: int = 0, n_chunks: int | None = None):
+        """(d_rp, d_rg) in bead units, [R, n, 2]."""
+        n = self.n_chunks - chunk_begin if n_chunks is None else n_chunks
+        out = np.empty((self.R, n, 2))
+        self._check(self.lib.esb_get_raw_distances(self.h, chunk_begin, n, _dp(out)))
+        return out
 
     def status(self):
         st = np.empty(self.R, np.int32)

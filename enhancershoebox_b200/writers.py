@@ -1,0 +1,101 @@
+"""On-disk outputs of the reference drivers, written from the device's frame records.
+
+Formats follow ``run_single_shoebox.py`` (== ``VisitorGeneMaps/run_single_GENES_STAGES.py``):
+``run<r>/geneTrack.txt`` (:1496), ``run<r>/ser5pAroundCluster.txt`` (:743-748, 1578-1590), the event
+log (:1595-1617), ``parallel_counter/run<r>.txt`` (:1619-1621), ``active_duration.txt`` (:1625-1627),
+``gene_stats.txt`` (:1629-1642), ``{dist,ddist}_{induced,approaching,active,receding}.txt``
+(:1644-1664) and the completion sentinel ``run<r>/figures/ser5p_cluster.pdf`` that the launcher polls
+(``run_parallel_shoebox.sh:8-11,69-75``).  All numbers are printed with ``str()`` as the reference does.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import protocol as P
+
+EVENT_TYPES = ["induced", "approaching", "active", "receding"]
+W1 = W2 = 20
+
+
+def make_run_folders(out_folder: str, run_number: int, subfolders=("figures", "image_files", "microscopy_files")) -> str:
+    """run_single_shoebox.py:308-317."""
+    os.makedirs(os.path.join(out_folder, "parallel_counter"), exist_ok=True)
+    run_dir = os.path.join(out_folder, f"run{run_number}")
+    os.makedirs(run_dir, exist_ok=True)
+    for s in subfolders:
+        os.makedirs(os.path.join(run_dir, s), exist_ok=True)
+    return run_dir
+
+
+def gene_track_lines(frames: np.ndarray):
+    """frames [n_chunks, 9] -> the lines of geneTrack.txt (:1496)."""
+    for f in frames:
+        yield (str(float(f[0])) + "," + str(float(f[1])) + "," + str(float(f[2])) + "," + str(float(f[3])) + "," + str(float(f[4])) + ","
+               + str(float(f[5])) + "," + str(int(f[6])) + "," + str(int(f[7])) + "," + str(int(f[8])) + "\n")
+
+
+def cluster_header() -> str:
+    """:743-748."""
+    r = P.CLUSTER_R[1:]
+    return "t," + ",".join(str(v) for v in r) + "\n"
+
+
+def event_log(states: np.ndarray) -> list:
+    """:1595-1617.  0 induced but non-engaging, 1 approaching (w1 before), 2 active, 3 receding (w2 after)."""
+    n = len(states)
+    active_runs = {i for i in range(n) if int(states[i]) == 2}
+    ev = [0] * n
+    for i in range(n - 1):
+        if i in active_runs:
+            ev[i + 1] = 2
+    for i in range(n):
+        if (i - W2) >= 0:
+            if ev[i - W2] == 2:
+                if ev[i] != 2:
+                    ev[i] = 3
+        if (i + W1) <= (n - 1):
+            if ev[i + W1] == 2:
+                if ev[i] != 2:
+                    ev[i] = 1
+    return ev
+
+
+def write_run(out_folder: str, run_number: int, frames: np.ndarray, hist: np.ndarray, raw: np.ndarray, total_active_steps: int,
+              n_runs: int = P.N_RUNS, subfolders=("figures", "image_files", "microscopy_files")) -> None:
+    """Everything one repeat leaves on disk.  frames [n,9], hist [n,49], raw [n,2] = (d_rp, d_rg) in bead units."""
+    run_dir = make_run_folders(out_folder, run_number, subfolders)
+    with open(os.path.join(run_dir, "geneTrack.txt"), "w") as f:
+        f.writelines(gene_track_lines(frames))
+    with open(os.path.join(run_dir, "ser5pAroundCluster.txt"), "w") as f:
+        f.write(cluster_header())
+        for i in range(len(frames)):
+            f.write(str((i + 1) * P.DELT) + "," + ",".join(str(int(v)) for v in hist[i]) + "\n")
+    ev = event_log(frames[:, 8])
+    with open(os.path.join(out_folder, "parallel_counter", f"run{run_number}.txt"), "w") as f:
+        f.write("Run " + str(run_number) + " done!\n")
+    prog = os.path.join(out_folder, "parallel_counter", f"progress_run{run_number}.txt")
+    if os.path.exists(prog):
+        os.remove(prog)
+    with open(os.path.join(out_folder, "active_duration.txt"), "a") as f:
+        f.write(f"{run_number},{total_active_steps},{n_runs - P.T_INDUCTION_ON}\n")
+    with open(os.path.join(out_folder, "gene_stats.txt"), "a") as f:
+        for j in range(len(frames)):
+            if j < P.T_INDUCTION_ON:
+                continue
+            d = float(raw[j, 1])
+            in_contact = 1 if d < P.POL2_RELEASE_RADIUS else 0
+            s2p = 1 if ev[j] == 2 else 0
+            f.write(str(in_contact) + "," + str(d * P.SIG_CHROMATIN_NM) + "," + str(int(frames[j, 7])) + "," + str(s2p) + "\n")
+    dist = [float(raw[x, 1]) * P.SIG_CHROMATIN_NM for x in range(len(frames))]
+    ddist = [dist[k + 1] - dist[k] for k in range(len(dist) - 1)]
+    for name, arr in (("dist", dist), ("ddist", ddist)):
+        for j, ev_name in enumerate(EVENT_TYPES):
+            with open(os.path.join(out_folder, f"{name}_{ev_name}.txt"), "a") as f:
+                for i in range(len(arr)):
+                    if ev[i] == j:
+                        f.write(str(arr[i]) + "\n")
+    # completion sentinel the launcher waits for (it deletes the file afterwards)
+    with open(os.path.join(run_dir, "figures", "ser5p_cluster.pdf"), "wb") as f:
+        f.write(b"%PDF-1.1\n% placeholder written by shoebox-b200: plots are out of scope, the launcher only needs the file\n%%EOF\n")

@@ -147,6 +147,9 @@ int esb_forces(esb_handle *h, int pair_mode, int map_id, double soft_a, int with
 /* geneTrack records: out [R][n_chunks][9] doubles (t, probe xyz*60, d_rp*60, d_rg*60, n_s5p_prom,
  * n_s5p_gene, state) (run_single_shoebox.py:1496); hist [R][n_chunks][49] ints or NULL (:1504-1519) */
 int esb_get_frames(esb_handle *h, int chunk_begin, int n_chunks, double *out, int *hist);
+/* d_rp, d_rg of the same frames in bead units, out [R][n_chunks][2]: gene_stats.txt tests d_rg < 3
+ * before scaling by 60 nm (run_single_shoebox.py:1629-1642) */
+int esb_get_raw_distances(esb_handle *h, int chunk_begin, int n_chunks, double *out);
 /* same records, asynchronously on `stream` into a caller-pinned buffer (no histograms) */
 int esb_get_frames_async(esb_handle *h, int chunk_begin, int n_chunks, double *out, void *stream);
 int esb_get_status(esb_handle *h, int *status);                   /* [R] ESB_ST_* bits               */
