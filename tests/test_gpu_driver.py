@@ -32,7 +32,8 @@ def test_driver_writes_reference_layout_and_aggregates(tmp_path, monkeypatch):
         frames.append(rows)
         assert len(open(os.path.join(run, "ser5pAroundCluster.txt")).read().split("\n")) == n_chunks + 2
     frames = np.array(frames)
-    assert np.all(frames[:, :150, 8] == 0) and np.all(frames[:, 150:, 8] >= 1)
+    assert np.all(frames[:, :150, 8] == 0) and np.all(frames[:, 150, 8] >= 1)      # induced from i = 150 on
+    assert (frames[:, 150:, 8] == 0).sum() <= 10 * 2                              # only the single frame on which a gene is inactivated
     assert (frames[:, :, 8] == 2).sum() > 0                                       # -x 5 -a 1000: genes do activate
     assert len(open(os.path.join(out, "active_duration.txt")).read().split("\n")) == 11
     assert len(open(os.path.join(out, "gene_stats.txt")).read().split("\n")) == 10 * (n_chunks - 150) + 1
