@@ -9,7 +9,12 @@
 
 #include "../../include/esb.h"
 
+#ifndef ESB_THREADS
 #define ESB_THREADS 256
+#endif
+#ifndef ESB_MIN_CTAS
+#define ESB_MIN_CTAS 3                  // resident CTAs per SM the step kernel is compiled for
+#endif
 #define ESB_G 8                      // lanes cooperating on one atom (pair loop and list build)
 #define ESB_GROUPS (ESB_THREADS / ESB_G)
 #define ESB_MAX_TERMS 8              // bonded terms per atom (linear chain: 2 bonds + 3 angles)

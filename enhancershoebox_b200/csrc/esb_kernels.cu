@@ -10,6 +10,8 @@
 // offset is an immediate; the phases are separate __noinline__ functions (each gets the full
 // register budget) that take the __grid_constant__ kernel arguments by reference.
 // Reference semantics (what each phase stands in for) are cited at the device functions.
+#include <type_traits>
+
 #include "esb_device.cuh"
 
 namespace {
@@ -28,9 +30,9 @@ struct Smem {
     unsigned short *sidx;        // [n_pad]       atom indices sorted by slot
 };
 
-enum { M_POOLCUR = 0, M_FAIL, M_PAIRS, M_CURLIST, M_SCAN /* 8 warps */,
-       M_CNT_PROM = M_SCAN + 8, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */, M_END = M_HIST + 52 };
-static_assert(ESB_THREADS == 256, "scan scratch assumes 8 warps");
+enum { M_POOLCUR = 0, M_FAIL, M_PAIRS, M_CURLIST, M_SCAN /* one per warp */,
+       M_CNT_PROM = M_SCAN + ESB_THREADS / 32, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */, M_END = M_HIST + 52 };
+static_assert((ESB_NL_MAXNB + 1) % ESB_THREADS == 0, "length-sort scan: equal share of counters per thread");
 enum { D_RR = 0, D_PROBE = 3, D_GENE = 6, D_END = 10 };
 
 __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables)
@@ -208,40 +210,64 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
             z0 = min(z0, max(cz - rng, 0)); z1 = max(z1, min(cz + rng, ncz - 1));
             any_topo |= ia[b] < n_topo;
         }
-        for (int zz = z0; zz <= z1; zz++)
-            for (int yy = y0; yy <= y1; yy++) {
-                const int row = (zz * ncy + yy) * ncx;
-                const int s_first = (row + x0) * ESB_NCLASS;
-                const int ka = s_first ? S.cend[s_first - 1] : 0;
-                const int kb = S.cend[(row + x1) * ESB_NCLASS + ESB_NCLASS - 1];
-                for (int k0 = ka; k0 < kb; k0 += 32) {
-                    const int k = k0 + lane;
-                    const bool live = k < kb;
-                    const int j = live ? S.sidx[k] : 0;
-                    const float4 pj = S.pos[j];
-                    const int tj = __float_as_int(pj.w) & 0xff;
-                    const bool topo_j = any_topo && j < n_topo;
+        // Two warp-uniform specialisations keep the common inner loop short: `uniform` = the four beads
+        // have the same type (one cutoff / table-id row per candidate), `any_topo` = some bead of the quad
+        // is bonded (only then can a candidate be an excluded 1-2/1-3/1-4 partner).
+        const bool uniform = (ta[0] == ta[1]) && (ta[1] == ta[2]) && (ta[2] == ta[3]);
+        unsigned int *outp[4];
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const float dx = pa[b].x - pj.x, dy = pa[b].y - pj.y, dz = pa[b].z - pj.z;
-                        const float r2 = dx * dx + dy * dy + dz * dz;
-                        bool ok = live && (r2 < S.setup->cutsq_skin[ta[b] * ESB_MAXT + tj]) && (j != ia[b]);
-                        if (ok && topo_j && ia[b] < n_topo) {
-                            const uint4 sp = *reinterpret_cast<const uint4 *>(a.spec + (size_t)ia[b] * ESB_MAX_SPEC);
-                            const unsigned int jj = (unsigned int)j;
-                            ok = !((sp.x & 0xffffu) == jj || (sp.x >> 16) == jj || (sp.y & 0xffffu) == jj || (sp.y >> 16) == jj ||
-                                   (sp.z & 0xffffu) == jj || (sp.z >> 16) == jj || (sp.w & 0xffffu) == jj || (sp.w >> 16) == jj);
+        for (int b = 0; b < 4; b++) outp[b] = pool + (size_t)ia[b] * ESB_NL_STRIDE;
+        const float *cs_row = S.setup->cutsq_skin;
+        const unsigned char *tab_row = S.setup->tabid;
+        auto scan_rows = [&](auto topo_tag, auto uniform_tag) {
+            constexpr bool TOPO = decltype(topo_tag)::value, UNIFORM = decltype(uniform_tag)::value;
+            for (int zz = z0; zz <= z1; zz++)
+                for (int yy = y0; yy <= y1; yy++) {
+                    const int row = (zz * ncy + yy) * ncx;
+                    const int s_first = (row + x0) * ESB_NCLASS;
+                    const int ka = s_first ? S.cend[s_first - 1] : 0;
+                    const int kb = S.cend[(row + x1) * ESB_NCLASS + ESB_NCLASS - 1];
+                    for (int k0 = ka; k0 < kb; k0 += 32) {
+                        const int k = k0 + lane;
+                        const bool live = k < kb;
+                        const int j = live ? S.sidx[k] : 0;
+                        const float4 pj = S.pos[j];
+                        const int tj = __float_as_int(pj.w) & 0xff;
+                        float cs_u = 0.0f;
+                        unsigned int ent_u = 0u;
+                        if (UNIFORM) {
+                            cs_u = cs_row[ta[0] * ESB_MAXT + tj];
+                            ent_u = (unsigned int)j | ((unsigned int)tab_row[ta[0] * ESB_MAXT + tj] << 16);
                         }
-                        const unsigned int bits = __ballot_sync(FULL, ok);
-                        if (ok) {
-                            const int slot = cnt[b] + __popc(bits & lt_mask);
-                            if (slot < ESB_NL_MAXNB)
-                                pool[(size_t)ia[b] * ESB_NL_STRIDE + slot] = (unsigned int)j | ((unsigned int)S.setup->tabid[ta[b] * ESB_MAXT + tj] << 16);
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const float dx = pa[b].x - pj.x, dy = pa[b].y - pj.y, dz = pa[b].z - pj.z;
+                            const float r2 = dx * dx + dy * dy + dz * dz;
+                            const float cs = UNIFORM ? cs_u : cs_row[ta[b] * ESB_MAXT + tj];
+                            bool ok = live && (r2 < cs) && (j != ia[b]);
+                            if (TOPO) {
+                                if (ok && j < n_topo && ia[b] < n_topo) {
+                                    const uint4 sp = *reinterpret_cast<const uint4 *>(a.spec + (size_t)ia[b] * ESB_MAX_SPEC);
+                                    const unsigned int jj = (unsigned int)j;
+                                    ok = !((sp.x & 0xffffu) == jj || (sp.x >> 16) == jj || (sp.y & 0xffffu) == jj || (sp.y >> 16) == jj ||
+                                           (sp.z & 0xffffu) == jj || (sp.z >> 16) == jj || (sp.w & 0xffffu) == jj || (sp.w >> 16) == jj);
+                                }
+                            }
+                            const unsigned int bits = __ballot_sync(FULL, ok);
+                            if (ok) {
+                                const int slot = cnt[b] + __popc(bits & lt_mask);
+                                if (slot < ESB_NL_MAXNB)
+                                    outp[b][slot] = UNIFORM ? ent_u : ((unsigned int)j | ((unsigned int)tab_row[ta[b] * ESB_MAXT + tj] << 16));
+                            }
+                            cnt[b] += __popc(bits);
                         }
-                        cnt[b] += __popc(bits);
                     }
                 }
-            }
+        };
+        using T_ = std::true_type;
+        using F_ = std::false_type;
+        if (any_topo) { if (uniform) scan_rows(T_{}, T_{}); else scan_rows(T_{}, F_{}); }
+        else { if (uniform) scan_rows(F_{}, T_{}); else scan_rows(F_{}, F_{}); }
         if (lane < 4) {
             const int idx = 4 * q + lane;
             int c = lane == 0 ? cnt[0] : lane == 1 ? cnt[1] : lane == 2 ? cnt[2] : cnt[3];
@@ -263,10 +289,11 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         __syncthreads();
         for (int k = tid; k < n; k += ESB_THREADS) atomicAdd(&hist[ESB_NL_MAXNB - (int)(qbuild[k].y >> 16)], 1);
         __syncthreads();
-        // exclusive scan of 1024 counters: 4 per thread
-        int v[4], s = 0;
+        // exclusive scan of the 1024 counters: an equal share per thread
+        constexpr int PER = (ESB_NL_MAXNB + 1) / ESB_THREADS;
+        int v[PER], s = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) { v[k] = hist[4 * tid + k]; s += v[k]; }
+        for (int k = 0; k < PER; k++) { v[k] = hist[PER * tid + k]; s += v[k]; }
         int incl = s;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -278,7 +305,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         int base = incl - s;
         for (int w = 0; w < warp; w++) base += S.misc[M_SCAN + w];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { hist[4 * tid + k] = base; base += v[k]; }
+        for (int k = 0; k < PER; k++) { hist[PER * tid + k] = base; base += v[k]; }
         __syncthreads();
         for (int k = tid; k < n; k += ESB_THREADS) {
             const uint2 d = qbuild[k];
@@ -722,7 +749,7 @@ __device__ __noinline__ void observe(const KArgs &a, int r, const esb_chunk_desc
 // leave 148*3 - (R mod 148*3) slots empty for the whole last wave).  The grid never exceeds the
 // number of co-resident CTAs, so a waiting CTA's producer is always running.
 template <int NP>
-__global__ void __launch_bounds__(ESB_THREADS, 3)
+__global__ void __launch_bounds__(ESB_THREADS, ESB_MIN_CTAS)
 esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int n_chunks, const double delt, const double sig_nm,
                int *ticket, int *progress)
 {
