@@ -683,10 +683,11 @@ __device__ __noinline__ void observe(const KArgs &a, int r, const esb_chunk_desc
                 S.pos[first + k] = q;
             }
         };
-        const bool on = i >= 150;  // t_induction_on == t_activation_on (:472-475)
+        // which of the three processes run in this chunk is the host's decision (t_induction_on ==
+        // t_activation_on == 150, :472-475; Flavopiridol stops activation at NRuns, :885-886)
         if (rs.gene_state == 2) { rs.duration++; rs.total_active++; }
-        if (on && rs.gene_state == 0) { set_types(g, 5, 6); rs.gene_state = 1; }
-        if (on && rs.gene_state == 1 && n_prom > rs.threshold) {
+        if (d.induce_on && rs.gene_state == 0) { set_types(g, 5, 6); rs.gene_state = 1; }
+        if (d.activate_on && rs.gene_state == 1 && n_prom > rs.threshold) {
             uint32_t o[4];
             philox4x32_10((uint32_t)i, 0u, 0u, 1u, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), o);
             const double u = (double)(o[0] >> 8) * 0x1p-24;
@@ -696,7 +697,7 @@ __device__ __noinline__ void observe(const KArgs &a, int r, const esb_chunk_desc
             if (rs.delay < 2) rs.delay++;
             else { rs.marked = 0; set_types(g, 5, 7); set_types(g - p, p, 11); }
         }
-        if (on && rs.gene_state == 2 && rs.duration >= 50) {
+        if (d.inactivate_on && rs.gene_state == 2 && rs.duration >= 50) {
             rs.duration = 0; set_types(g, 5, 2); set_types(g - p, p, 10); rs.gene_state = 0;
         }
         // --- RBP -> RNP ramp (:1457-1470) ---

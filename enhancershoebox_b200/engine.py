@@ -39,7 +39,8 @@ class ChunkDesc(C.Structure):
     _fields_ = [("chunk_index", C.c_int), ("n_steps", C.c_int), ("pair_mode", C.c_int), ("map_id", C.c_int),
                 ("ramp_on", C.c_int), ("ramp_start", C.c_int64), ("ramp_stop", C.c_int64),
                 ("adapt_soft", C.c_int), ("adapt_bond1", C.c_int), ("adapt_bond2", C.c_int),
-                ("observe", C.c_int), ("expected_rnp", C.c_int)]
+                ("observe", C.c_int), ("expected_rnp", C.c_int),
+                ("induce_on", C.c_int), ("activate_on", C.c_int), ("inactivate_on", C.c_int)]
 
 
 _lib = None
@@ -286,6 +287,10 @@ class ShoeboxBatch:
             d.observe = int(observe)
             i = pl.index
             d.expected_rnp = int(((i + 1) * slope + c_rnp) * self.n_rbprnp) if (i + 1) >= P.T_INDUCTION_ON else -1
+            t_act_off = P.N_RUNS if self.condition == "Flavopiridol" else 2 * P.N_RUNS + 10 ** 6   # :482, 885-886
+            d.induce_on = int(i >= P.T_INDUCTION_ON)
+            d.activate_on = int(P.T_INDUCTION_ON <= i < t_act_off)
+            d.inactivate_on = int(i >= P.T_INDUCTION_ON)
         self._check(self.lib.esb_set_schedule(self.h, len(plans), descs))
         self.n_chunks = len(plans)
         self.plans = list(plans)
@@ -352,6 +357,11 @@ class ShoeboxBatch:
 
     def device_ptr(self, which: int) -> int:
         return int(self.lib.esb_device_ptr(self.h, which) or 0)
+
+
+def aggregate_all(frames: np.ndarray, contact_dist: float = 250.0, t_skip: int = 150, device: int = 0):
+    """dist_genestages_all.py: one row per run (VGM/dist_genestages_all.py:66-85) = groups of one."""
+    return aggregate_grouped(frames, 1, contact_dist, t_skip, device)
 
 
 def aggregate_grouped(frames: np.ndarray, group: int = 5, contact_dist: float = 250.0, t_skip: int = 150, device: int = 0):

@@ -70,6 +70,9 @@ typedef struct {
     int adapt_bond2;        /* fix s3: bond r0 type 2 ramp(0.033,0.3), every 10 (:638-639)   */
     int observe;            /* 1: measurements + gene state machine + frame record          */
     int expected_rnp;       /* int(f_rnp*len(rbprnp_atoms)) for this chunk, -1: no ramp (:1457-1460) */
+    int induce_on;          /* i >= t_induction_on and i < t_induction_off                    (:1304)      */
+    int activate_on;        /* i >= t_activation_on and i < t_activation_off (Flavopiridol: off from NRuns, :885-886, 1322) */
+    int inactivate_on;      /* i >= t_activation_on                                           (:1380)      */
 } esb_chunk_desc;
 
 const char *esb_last_error(void);

@@ -95,6 +95,7 @@ class GeneMachine:
     t_induction_on: int = 150
     activation_delay: int = 2
     t_active_duration: int = 50
+    t_activation_off: int = 10 ** 9   # Flavopiridol sets it to NRuns (run_single_shoebox.py:885-886)
     state: int = 0            # 0 inactive, 1 induced, 2 active(-listed)
     marked: bool = False
     delay: int = 0
@@ -115,7 +116,7 @@ class GeneMachine:
         if i >= self.t_induction_on and self.state == 0:      # :1304-1312
             types[g:g + LENGTH_GENE] = T_INDUCED
             self.state = 1
-        if i >= self.t_induction_on and self.state == 1:      # :1322-1345
+        if self.t_induction_on <= i < self.t_activation_off and self.state == 1:      # :1322-1345
             if n_prom > self.threshold:
                 u = O.lib().esbo_u32_to_unit(O.philox((i, 0, 0, 1), self.key)[0])
                 if not (u > self.p_activation):
