@@ -36,6 +36,7 @@ def test_actin_batch_runs_and_matches_oracle(oracle_lib, actin_setup):
     # force parity at the equilibrated actin state (table phase B of the shoebox driver)
     orc = oracle_lib.Oracle(d, pt, lookup, seed=3)
     orc.set_state(t[0], x[0], v[0])
+    orc.L.esbo_set_bond_coeff(orc.h, 1, P.BOND_K, float(eng.bond_r0()[1]))      # fix adapt left r0 = 0.9033 behind
     orc.set_pair("B")
     fo, eo, st = orc.forces()
     fg, eg = eng.forces("B")
