@@ -146,7 +146,7 @@ int rebuild_setups(esb_handle *h)
 {
     if (!h->have_box) return fail(ESB_ESTATE, "esb_set_box must be called first");
     // ---- cell grid: the build scratch (the 3 force arrays) must hold the cell table + the sorted index ----
-    const int cap = 5 * h->n_pad - 32;
+    const int cap = 4 * h->n_pad - 32;    // scratch = 12 n_pad bytes: slot table (2 B/slot) + two u16 index arrays
     double c = h->cell_edge;
     for (;;) {
         h->ncx = std::max(1, (int)ceil((h->hi[0] - h->lo[0]) / c));

@@ -159,22 +159,24 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         for (int c = b0; c < b1; c++) { base += S.cend[c]; S.cend[c] = (unsigned short)base; }
     }
     __syncthreads();
-    // scatter: cend[s] (= start of s) is the cursor of slot s; afterwards cend[s] = end of s
+    // scatter: cend[s] (= start of s) is the cursor of slot s; afterwards cend[s] = end of s.  The order
+    // inside a slot is whatever the atomics produced; `tmp` holds it until the rank sort below.
+    unsigned short *tmp = S.sidx + a.n_pad;
     for (int i = tid; i < n; i += ESB_THREADS) {
         const int slot = slot_of(a, S.pos[i]);
         const unsigned int old = atomicAdd(&cw[slot >> 1], 1u << (16 * (slot & 1)));
-        S.sidx[(old >> (16 * (slot & 1))) & 0xffffu] = (unsigned short)i;
+        tmp[(old >> (16 * (slot & 1))) & 0xffffu] = (unsigned short)i;
     }
     __syncthreads();
-    // order every slot by atom index (insertion sort; slots hold a handful of beads)
-    for (int c = tid; c < nslots; c += ESB_THREADS) {
-        const int s0 = c ? S.cend[c - 1] : 0, s1 = S.cend[c];
-        for (int p = s0 + 1; p < s1; p++) {
-            const unsigned short v = S.sidx[p];
-            int q = p - 1;
-            while (q >= s0 && S.sidx[q] > v) { S.sidx[q + 1] = S.sidx[q]; q--; }
-            S.sidx[q + 1] = v;
-        }
+    // order every slot by atom index (deterministic lists): one thread per bead counts the beads of its
+    // slot with a smaller index -- O(sum n_s^2) comparisons spread over the CTA instead of one thread
+    // insertion-sorting the 100+ beads of a dense slot while the others wait
+    for (int i = tid; i < n; i += ESB_THREADS) {
+        const int slot = slot_of(a, S.pos[i]);
+        const int s0 = slot ? S.cend[slot - 1] : 0, s1 = S.cend[slot];
+        int rank = 0;
+        for (int p = s0; p < s1; p++) rank += (tmp[p] < (unsigned short)i);
+        S.sidx[s0 + rank] = (unsigned short)i;
     }
     __syncthreads();
 
