@@ -324,7 +324,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     }
     const size_t tot = (size_t)n_replicas * h->n_pad;
     if ((rc = dev_alloc(&h->d_pos4, tot)) || (rc = dev_alloc(&h->d_vel4, tot)) || (rc = dev_alloc(&h->d_rs, (size_t)n_replicas)) ||
-        (rc = dev_alloc(&h->d_frozen, (size_t)h->n_pad)) || (rc = dev_alloc(&h->d_nl_pool, (size_t)n_replicas * h->n_pad * ESB_NL_STRIDE + 256)) ||
+        (rc = dev_alloc(&h->d_frozen, (size_t)h->n_pad)) || (rc = dev_alloc(&h->d_nl_pool, (size_t)n_replicas * h->n_pad * ESB_NL_STRIDE + 1024)) ||
         (rc = dev_alloc(&h->d_nl_qinfo, 2 * tot)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * ESB_N_COUNTERS)) || (rc = dev_alloc(&h->d_sched, (size_t)n_replicas + 1))) {
         esb_destroy(h);
         return rc;

@@ -12,6 +12,9 @@
 #ifndef ESB_THREADS
 #define ESB_THREADS 256
 #endif
+#ifndef ESB_PREFETCH
+#define ESB_PREFETCH 4                  // neighbour-list entries each lane keeps in flight (even)
+#endif
 #ifndef ESB_MIN_CTAS
 #define ESB_MIN_CTAS 3                  // resident CTAs per SM the step kernel is compiled for
 #endif

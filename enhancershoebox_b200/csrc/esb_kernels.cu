@@ -486,17 +486,19 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                 fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
             }
         };
-        unsigned int w0 = __ldcg(lp), w1 = __ldcg(lp + ESB_G), w2 = __ldcg(lp + 2 * ESB_G), w3 = __ldcg(lp + 3 * ESB_G);
-        for (int e0 = 0; e0 < cnt_max; e0 += 4 * ESB_G) {
-            const int e = e0 + gl;
-            lp += 4 * ESB_G;
-            const unsigned int c0 = w0, c1 = w1;
-            w0 = __ldcg(lp); w1 = __ldcg(lp + ESB_G);
-            pair_body(c0, e); pair_body(c1, e + ESB_G);
-            if (e0 + 2 * ESB_G >= cnt_max) break;
-            const unsigned int c2 = w2, c3 = w3;
-            w2 = __ldcg(lp + 2 * ESB_G); w3 = __ldcg(lp + 3 * ESB_G);
-            pair_body(c2, e + 2 * ESB_G); pair_body(c3, e + 3 * ESB_G);
+        constexpr int DEPTH = ESB_PREFETCH;                       // list entries in flight per lane
+        unsigned int w[DEPTH];
+#pragma unroll
+        for (int k = 0; k < DEPTH; k++) w[k] = __ldcg(lp + k * ESB_G);
+        for (int e0 = 0; e0 < cnt_max; e0 += DEPTH * ESB_G) {
+            lp += DEPTH * ESB_G;
+#pragma unroll
+            for (int k = 0; k < DEPTH; k += 2) {
+                if (k > 0 && e0 + k * ESB_G >= cnt_max) break;
+                const unsigned int c0 = w[k], c1 = w[k + 1];
+                w[k] = __ldcg(lp + k * ESB_G); w[k + 1] = __ldcg(lp + (k + 1) * ESB_G);
+                pair_body(c0, e0 + k * ESB_G + gl); pair_body(c1, e0 + (k + 1) * ESB_G + gl);
+            }
         }
 #pragma unroll
         for (int d = ESB_G >> 1; d >= 1; d >>= 1) {
