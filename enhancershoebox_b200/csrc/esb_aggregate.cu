@@ -195,6 +195,95 @@ __global__ void __launch_bounds__(AGG_THREADS) esb_aggregate_kernel(const AggArg
 }
 
 
+
+// ------------------------------------------------------------------------------------------------
+// Per-run statistics of VisitorGeneMaps/dist_genestages_grouped_5percentile_10xaveraging.py:78-89
+// (also the rows of dist_genestages_all_5percentile.py): mean Ser5P count, S2PInt, Contact, mean
+// activation distance (NaN when the gene never activates) and np.percentile(d[t_skip:], q) of d_rg
+// and d_rp.  The percentile is numpy's default 'linear' method: the host passes the lower order
+// statistic `prev` and the interpolation weight `gamma` computed with numpy's own expression; here
+// the tail is bitonic-sorted in shared memory and numpy's _lerp is applied.
+// ------------------------------------------------------------------------------------------------
+struct RunArgs {
+    const double *frames;   // [n_runs][n_frames][9]
+    double *scratch;        // [n_runs][n_frames]
+    double *out;            // [n_runs][6]
+    int n_frames, t_skip, prev, npow2;
+    double contact_dist, gamma;
+};
+
+__device__ double np_lerp(const double a, const double b, const double t)
+{
+    const double diff = __dsub_rn(b, a);
+    if (t >= 0.5) return __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, t)));
+    return __dadd_rn(a, __dmul_rn(diff, t));
+}
+
+__global__ void __launch_bounds__(AGG_THREADS) esb_aggregate_runs_kernel(const RunArgs a)
+{
+    extern __shared__ double s_sort[];
+    __shared__ long long s_off[AGG_MAX_LEAVES + 1];
+    __shared__ double s_sum[AGG_MAX_LEAVES];
+    __shared__ int s_nl, s_cnt[2], s_scan[AGG_THREADS];
+    const int run = blockIdx.x, tid = threadIdx.x, L = a.n_frames;
+    const double *f = a.frames + (size_t)run * L * ESB_FRAME_DOUBLES;
+    double *o = a.out + (size_t)run * 6;
+    if (tid < 2) s_cnt[tid] = 0;
+    __syncthreads();
+    int nj = 0, nc = 0;
+    for (int k = tid; k < L; k += AGG_THREADS) {
+        if (k >= 1 && (int)f[(size_t)k * 9 + 8] == 2) nj++;
+        if (f[(size_t)k * 9 + 4] < a.contact_dist) nc++;
+    }
+    if (nj) atomicAdd(&s_cnt[0], nj);
+    if (nc) atomicAdd(&s_cnt[1], nc);
+    __syncthreads();
+    if (tid == 0) {
+        o[1] = __ddiv_rn((double)(100LL * s_cnt[0]), (double)(L - a.t_skip));
+        o[2] = __ddiv_rn((double)(100LL * s_cnt[1]), (double)L);
+    }
+    auto get_s5p = [&](long long k) { return f[(size_t)k * 9 + 6]; };
+    const double s5p_mean = block_pairwise_mean(get_s5p, (long long)L, s_off, s_sum, &s_nl);
+    // activation onsets in frame order
+    double *scr = a.scratch + (size_t)run * L;
+    const int seg = (L + AGG_THREADS - 1) / AGG_THREADS;
+    const int k0 = tid * seg, k1 = min(k0 + seg, L);
+    int mine = 0;
+    for (int k = max(k0, 1); k < k1; k++)
+        if ((int)f[(size_t)k * 9 + 8] == 2 && (int)f[(size_t)(k - 1) * 9 + 8] != 2) mine++;
+    s_scan[tid] = mine;
+    __syncthreads();
+    if (tid == 0) { int acc = 0; for (int t = 0; t < AGG_THREADS; t++) { const int c = s_scan[t]; s_scan[t] = acc; acc += c; } s_cnt[0] = acc; }
+    __syncthreads();
+    int w = s_scan[tid];
+    for (int k = max(k0, 1); k < k1; k++)
+        if ((int)f[(size_t)k * 9 + 8] == 2 && (int)f[(size_t)(k - 1) * 9 + 8] != 2) scr[w++] = f[(size_t)k * 9 + 4];
+    __syncthreads();
+    auto get_scr = [&](long long k) { return scr[k]; };
+    const double dist_mean = block_pairwise_mean(get_scr, (long long)s_cnt[0], s_off, s_sum, &s_nl);
+    if (tid == 0) { o[0] = s5p_mean; o[3] = dist_mean; }
+    // percentiles of columns 5 (d_rg) and 4 (d_rp) over frames t_skip..L-1
+    const int n = L - a.t_skip;
+    for (int which = 0; which < 2; which++) {
+        const int col = which == 0 ? 5 : 4;
+        for (int k = tid; k < a.npow2; k += AGG_THREADS) s_sort[k] = k < n ? f[(size_t)(k + a.t_skip) * 9 + col] : __longlong_as_double(0x7ff0000000000000LL);
+        __syncthreads();
+        for (int size = 2; size <= a.npow2; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int k = tid; k < a.npow2 / 2; k += AGG_THREADS) {
+                    const int lo = 2 * k - (k & (stride - 1));
+                    const int hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const double x = s_sort[lo], y = s_sort[hi];
+                    if ((x > y) == up) { s_sort[lo] = y; s_sort[hi] = x; }
+                }
+                __syncthreads();
+            }
+        if (tid == 0) o[4 + which] = np_lerp(s_sort[a.prev], s_sort[min(a.prev + 1, n - 1)], a.gamma);
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 extern "C" int esb_aggregate_grouped(int device, const double *frames, int frames_on_device, int n_runs, int n_frames,
@@ -223,6 +312,41 @@ extern "C" int esb_aggregate_grouped(int device, const double *frames, int frame
         esb_aggregate_kernel<<<n_groups, AGG_THREADS, 0, st>>>(a);
         if (cudaGetLastError() != cudaSuccess) { rc = ESB_ECUDA; break; }
         if (cudaMemcpyAsync(out, d_out, (size_t)n_groups * 4 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = ESB_ECUDA; break; }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = ESB_ECUDA; break; }
+    } while (0);
+    cudaFree(d_frames); cudaFree(d_scr); cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int esb_aggregate_runs(int device, const double *frames, int frames_on_device, int n_runs, int n_frames,
+                                  double contact_dist, int t_skip, int prev_index, double gamma, double *out, void *stream)
+{
+    if (!frames || !out || n_runs < 1 || n_frames < 2 || n_frames <= t_skip + 1 || prev_index < 0 || prev_index >= n_frames - t_skip) return ESB_EINVAL;
+    if ((long long)n_frames > (long long)AGG_MAX_LEAVES * 64) return ESB_EINVAL;
+    int npow2 = 1;
+    while (npow2 < n_frames - t_skip) npow2 <<= 1;
+    const size_t smem = (size_t)npow2 * sizeof(double);
+    if (smem > 160 * 1024) return ESB_EINVAL;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return ESB_ENODEV;
+    if (cudaSetDevice(device) != cudaSuccess) return ESB_ECUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nd = (size_t)n_runs * n_frames;
+    double *d_frames = nullptr, *d_scr = nullptr, *d_out = nullptr;
+    int rc = ESB_OK;
+    do {
+        if (!frames_on_device) {
+            if (cudaMalloc(&d_frames, nd * 9 * sizeof(double)) != cudaSuccess) { rc = ESB_ENOMEM; break; }
+            if (cudaMemcpyAsync(d_frames, frames, nd * 9 * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = ESB_ECUDA; break; }
+        }
+        if (cudaMalloc(&d_scr, nd * sizeof(double)) != cudaSuccess || cudaMalloc(&d_out, (size_t)n_runs * 6 * sizeof(double)) != cudaSuccess) { rc = ESB_ENOMEM; break; }
+        RunArgs a;
+        a.frames = frames_on_device ? frames : d_frames; a.scratch = d_scr; a.out = d_out;
+        a.n_frames = n_frames; a.t_skip = t_skip; a.prev = prev_index; a.npow2 = npow2; a.contact_dist = contact_dist; a.gamma = gamma;
+        if (cudaFuncSetAttribute(esb_aggregate_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { rc = ESB_ECUDA; break; }
+        esb_aggregate_runs_kernel<<<n_runs, AGG_THREADS, smem, st>>>(a);
+        if (cudaGetLastError() != cudaSuccess) { rc = ESB_ECUDA; break; }
+        if (cudaMemcpyAsync(out, d_out, (size_t)n_runs * 6 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = ESB_ECUDA; break; }
         if (cudaStreamSynchronize(st) != cudaSuccess) { rc = ESB_ECUDA; break; }
     } while (0);
     cudaFree(d_frames); cudaFree(d_scr); cudaFree(d_out);

@@ -82,6 +82,8 @@ _SIGNATURES = {
     "esb_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
     "esb_aggregate_grouped": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                         C.POINTER(C.c_double), C.c_void_p]),
+    "esb_aggregate_runs": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
+                                     C.POINTER(C.c_double), C.c_void_p]),
 }
 ABI_SYMBOLS = tuple(_SIGNATURES)
 
@@ -375,3 +377,44 @@ def aggregate_grouped(frames: np.ndarray, group: int = 5, contact_dist: float = 
     if rc != 0:
         raise EsbError(f"esb_aggregate_grouped failed with {rc}")
     return out
+
+
+def _linear_percentile_index(n: int, q: float):
+    """Lower order statistic and weight of numpy's default ('linear') percentile for n samples:
+    virtual index = n*q + (alpha + q*(1 - alpha - beta)) - 1 with alpha = beta = 1, evaluated like
+    numpy.lib._function_base_impl._compute_virtual_index does."""
+    quant = np.true_divide(q, 100)
+    alpha = beta = 1
+    vi = n * quant + (alpha + quant * (1 - alpha - beta)) - 1
+    prev = int(np.floor(vi))
+    return prev, float(vi - prev)
+
+
+def aggregate_runs(frames: np.ndarray, q: float = 5.0, contact_dist: float = 250.0, t_skip: int = 150, device: int = 0):
+    """Per-run rows [n_runs, 6]: S5PInt, S2PInt, Contact, DistActivation, q-percentile of d_rg[t_skip:] and of
+    d_rp[t_skip:] (VGM/dist_genestages_grouped_5percentile_10xaveraging.py:78-89)."""
+    lib = load_library()
+    fr = np.ascontiguousarray(frames, np.float64)
+    n_runs, n_frames = fr.shape[0], fr.shape[1]
+    prev, gamma = _linear_percentile_index(n_frames - t_skip, q)
+    out = np.empty((n_runs, 6))
+    rc = lib.esb_aggregate_runs(device, fr.ctypes.data_as(C.c_void_p), 0, n_runs, n_frames, contact_dist, t_skip, prev, gamma, _dp(out), None)
+    if rc != 0:
+        raise EsbError(f"esb_aggregate_runs failed with {rc}")
+    return out
+
+
+def aggregate_percentile_10x(frames: np.ndarray, group: int = 10, **kw):
+    """Rows of dist_genestages_grouped_5percentile_10xaveraging.py: np.nanmean of the per-run statistics over
+    consecutive groups of 10 runs, plus one row for the remainder (:94-141).  Returns (labels, rows[., 6])."""
+    import warnings
+    per_run = aggregate_runs(frames, **kw)
+    labels, rows = [], []
+    n = per_run.shape[0]
+    for lo in range(0, n, group):
+        hi = min(lo + group, n)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rows.append([np.nanmean(list(per_run[lo:hi, c])) for c in range(6)])
+        labels.append(f"{lo + 1}-{hi}")
+    return labels, np.array(rows).reshape(-1, 6)

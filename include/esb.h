@@ -176,6 +176,14 @@ void *esb_device_ptr(esb_handle *h, int which);
 int esb_aggregate_grouped(int device, const double *frames, int frames_on_device, int n_runs, int n_frames,
                           int group, double contact_dist, int t_skip, double *out, void *stream);
 
+/* Per-run rows of VGM/dist_genestages_grouped_5percentile_10xaveraging.py:78-89 (and of
+ * dist_genestages_all_5percentile.py): out [n_runs][6] = mean s5p_promoter, S2PInt, Contact, mean
+ * activation distance (NaN if none), np.percentile(d_rg[t_skip:], q), np.percentile(d_rp[t_skip:], q).
+ * prev_index/gamma: lower order statistic and weight of numpy's 'linear' percentile for that q and
+ * length (computed by the caller with numpy's own expression). */
+int esb_aggregate_runs(int device, const double *frames, int frames_on_device, int n_runs, int n_frames,
+                       double contact_dist, int t_skip, int prev_index, double gamma, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

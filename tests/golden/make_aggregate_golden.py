@@ -8,6 +8,7 @@ import os, runpy, sys, tempfile, types
 import numpy as np
 
 REF = '/root/reference/VisitorGeneMaps/dist_genestages_grouped.py'
+REF_PCT = '/root/reference/VisitorGeneMaps/dist_genestages_grouped_5percentile_10xaveraging.py'
 rng = np.random.default_rng(0)
 
 
@@ -63,17 +64,21 @@ def main():
     os.chdir(tmp)
     try:
         runpy.run_path(REF, run_name='__main__')
+        runpy.run_path(REF_PCT, run_name='__main__')          # the 5-percentile / 10x-averaged variant, same tree
     finally:
         os.chdir(cwd)
         os.listdir = real_listdir
     csv = open(os.path.join(tmp, 'summary_contact_grouped_Thresholds10-100_test.txt')).read()
-    out = {'csv': np.array(csv)}
+    csv_pct = open(os.path.join(tmp, 'summary_contact_grouped_Thresholds10-100_5percentile_10xaveraged.txt')).read()
+    out = {'csv': np.array(csv), 'csv_pct': np.array(csv_pct)}
     for (p, t, a), arr in frames.items():   # only the columns the aggregator reads are kept (size)
         out[f'drp_{p}_{t}_{a}'] = arr[:, :, 4]
+        out[f'drg_{p}_{t}_{a}'] = arr[:, :, 5]
         out[f's5p_{p}_{t}_{a}'] = arr[:, :, 6].astype(np.int16)
         out[f'state_{p}_{t}_{a}'] = arr[:, :, 8].astype(np.int8)
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'aggregate_golden.npz'), **out)
     print(csv)
+    print(csv_pct)
 
 
 if __name__ == '__main__':

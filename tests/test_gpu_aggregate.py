@@ -14,9 +14,9 @@ pytestmark = pytest.mark.gpu
 
 
 def _golden_frames(z, key):
-    d_rp, s5p, st = z["drp_" + key], z["s5p_" + key], z["state_" + key]
+    d_rp, d_rg, s5p, st = z["drp_" + key], z["drg_" + key], z["s5p_" + key], z["state_" + key]
     fr = np.zeros(d_rp.shape + (9,))
-    fr[:, :, 4], fr[:, :, 6], fr[:, :, 8] = d_rp, s5p, st
+    fr[:, :, 4], fr[:, :, 5], fr[:, :, 6], fr[:, :, 8] = d_rp, d_rg, s5p, st
     return fr
 
 
@@ -54,3 +54,32 @@ def test_ragged_and_empty_cases():
     fr[:, :, 4] = 100.0
     out = E.aggregate_grouped(fr)
     assert out[0, 1] == 100 * 399 / 250 and out[0, 2] == 100.0 and np.isnan(out[0, 3])
+
+
+def test_percentile_variant_against_reference_script_output():
+    """(f)3: per-run statistics + 5th percentiles on the device, 10x nanmean grouping on the host, against the CSV
+    of the unmodified dist_genestages_grouped_5percentile_10xaveraging.py."""
+    import pandas as pd
+    z = np.load(os.path.join(GOLDEN, "aggregate_golden.npz"))
+    df = pd.read_csv(io.StringIO(str(z["csv_pct"])), float_precision="round_trip")
+    cols = ["S5PInt", "S2PInt", "Contact", "DistActivation", "5percentRG", "5percentRP"]
+    for (p, t, a) in ((1, 10, 1), (2, 50, 10), (3, 80, 30)):
+        labels, rows = E.aggregate_percentile_10x(_golden_frames(z, f"{p}_{t}_{a}"))
+        sel = df[(df.Promoter == p) & (df.Threshold == t) & (df.Activation == a)]
+        assert labels == list(sel.Runs)
+        assert np.array_equal(rows, sel[cols].to_numpy(float), equal_nan=True), (p, t, a)
+
+
+@pytest.mark.parametrize("n_runs,n_frames,q", [(3, 152, 5), (4, 2000, 5), (2, 10000, 5), (3, 777, 50), (2, 1000, 99.5), (2, 400, 0), (2, 400, 100)])
+def test_per_run_rows_against_numpy(n_runs, n_frames, q):
+    rng = np.random.default_rng(n_runs * 7919 + n_frames)
+    fr = np.zeros((n_runs, n_frames, 9))
+    fr[:, :, 4] = rng.uniform(50, 900, (n_runs, n_frames))
+    fr[:, :, 5] = np.round(rng.uniform(50, 900, (n_runs, n_frames)))         # ties
+    fr[:, :, 6] = rng.integers(0, 120, (n_runs, n_frames))
+    st = rng.integers(0, 3, (n_runs, n_frames))
+    st[:, : n_frames // 3] = 0
+    st[0] = 0                                                                  # a run that never activates -> NaN
+    fr[:, :, 8] = st
+    out = E.aggregate_runs(fr, q=q)
+    assert np.array_equal(out, AGG.per_run_percentile(fr, q=q), equal_nan=True)

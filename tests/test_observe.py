@@ -108,9 +108,9 @@ def test_frame_line_format():
 
 
 def _golden_frames(z, key):
-    d_rp, s5p, st = z["drp_" + key], z["s5p_" + key], z["state_" + key]
+    d_rp, d_rg, s5p, st = z["drp_" + key], z["drg_" + key], z["s5p_" + key], z["state_" + key]
     fr = np.zeros(d_rp.shape + (9,))
-    fr[:, :, 4], fr[:, :, 6], fr[:, :, 8] = d_rp, s5p, st
+    fr[:, :, 4], fr[:, :, 5], fr[:, :, 6], fr[:, :, 8] = d_rp, d_rg, s5p, st
     return fr
 
 
@@ -127,6 +127,21 @@ def test_aggregate_oracle_equals_reference_script():
         assert rows.shape == ref.shape
         assert np.array_equal(rows, ref, equal_nan=True), (p, t, a)
     assert np.isnan(df[df.Promoter == 1].DistActivation).all()        # groups without any activation -> NaN
+
+
+def test_percentile_oracle_equals_reference_script():
+    """oracle/aggregate.percentile_10x against the CSV of the unmodified
+    dist_genestages_grouped_5percentile_10xaveraging.py (groups of 10 + the remainder row)."""
+    import pandas as pd
+    z = np.load(os.path.join(GOLDEN, "aggregate_golden.npz"))
+    df = pd.read_csv(io.StringIO(str(z["csv_pct"])), float_precision="round_trip")
+    assert len(df) == 3
+    cols = ["S5PInt", "S2PInt", "Contact", "DistActivation", "5percentRG", "5percentRP"]
+    for (p, t, a) in ((1, 10, 1), (2, 50, 10), (3, 80, 30)):
+        labels, rows = AGG.percentile_10x(_golden_frames(z, f"{p}_{t}_{a}"))
+        sel = df[(df.Promoter == p) & (df.Threshold == t) & (df.Activation == a)]
+        assert labels == list(sel.Runs)
+        assert np.array_equal(rows, sel[cols].to_numpy(float), equal_nan=True), (p, t, a)
 
 
 def test_reference_summary_tables_quantum():
