@@ -380,12 +380,10 @@ def aggregate_grouped(frames: np.ndarray, group: int = 5, contact_dist: float = 
 
 
 def _linear_percentile_index(n: int, q: float):
-    """Lower order statistic and weight of numpy's default ('linear') percentile for n samples:
-    virtual index = n*q + (alpha + q*(1 - alpha - beta)) - 1 with alpha = beta = 1, evaluated like
-    numpy.lib._function_base_impl._compute_virtual_index does."""
+    """Lower order statistic and weight of numpy's default ('linear') percentile for n samples: virtual index
+    (n - 1) * (q / 100), the expression of numpy.lib._function_base_impl._QuantileMethods['linear']."""
     quant = np.true_divide(q, 100)
-    alpha = beta = 1
-    vi = n * quant + (alpha + quant * (1 - alpha - beta)) - 1
+    vi = (n - 1) * quant
     prev = int(np.floor(vi))
     return prev, float(vi - prev)
 
