@@ -82,7 +82,7 @@ struct esb_handle {
     double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     bool have_box = false, have_topo = false, have_soft = false, have_tables = false, have_layout = false, have_state = false;
     bool setups_dirty = true;
-    double dt = 0.005, t_target = 1.0, t_damp = 0.5, wall_eps = 100.0, wall_cut = 3.0, skin = 0.3, cell_edge = 2.2;
+    double dt = 0.005, t_target = 1.0, t_damp = 0.5, wall_eps = 100.0, wall_cut = 3.0, skin = 0.3, cell_edge = 2.8, quad_edge = 2.2;
     int langevin_mode = 1;
     double bond_k[3] = {0, 90.0, 90.0}, bond_r0[3] = {0, 1.0, 0.3}, angle_k[3] = {0, 100.0 / 60.0, 33.0};
     double soft_cut[ESB_MAXT * ESB_MAXT];
@@ -114,7 +114,7 @@ struct esb_handle {
     int n_sm = 148;
     Layout lay = {0, 0, 0, 0};
     std::vector<ReplicaScalars> rs_host;
-    int ncx = 1, ncy = 1, ncz = 1;
+    int nry = 1, nrz = 1, qcx = 1, qcy = 1, qcz = 1;
 };
 
 namespace {
@@ -142,21 +142,37 @@ double closed_f_over_r(const esb_closed_form &cf, double r)
     return 24.0 * cf.eps_eff * r * r * r * r / s6 * (2.0 / (x * x * x) - 1.0 / (x * x));
 }
 
+// species classes of the row sort (run_single_shoebox.py:23-33): chromatin-like {1,2,9,10,11} 0, actin 3 -> 1,
+// RBP 4 -> 2, RNP 5 -> 3, Ser5P 8 -> 4, gene body while induced/active {6,7} -> 5 (the only chromatin types with
+// the long RNP cutoffs; kept apart so that they do not widen every chromatin search)
+const unsigned char k_class_of[ESB_MAXT] = {0, 0, 0, 1, 2, 3, 5, 5, 4, 0, 0, 0};
+
 int rebuild_setups(esb_handle *h)
 {
     if (!h->have_box) return fail(ESB_ESTATE, "esb_set_box must be called first");
-    // ---- cell grid: the build scratch (the 3 force arrays) must hold the cell table + the sorted index ----
-    const int cap = 4 * h->n_pad - 32;    // scratch = 12 n_pad bytes: slot table (2 B/slot) + two u16 index arrays
+    // ---- row grid of the list build: rows over (y, z) of edge row_edge, every row spans the box in x.
+    //      The build scratch (the 3 force arrays, 12 n_pad bytes) holds the (class, row) table (2 B per slot),
+    //      two u16 index arrays and the sorted x coordinates (4 B per bead): slots + 2 <= 2 n_pad.
+    const int cap = 2 * h->n_pad - 16;
     double c = h->cell_edge;
     for (;;) {
-        h->ncx = std::max(1, (int)ceil((h->hi[0] - h->lo[0]) / c));
-        h->ncy = std::max(1, (int)ceil((h->hi[1] - h->lo[1]) / c));
-        h->ncz = std::max(1, (int)ceil((h->hi[2] - h->lo[2]) / c));
-        if ((long long)h->ncx * h->ncy * h->ncz * ESB_NCLASS <= cap) break;
+        h->nry = std::max(1, (int)ceil((h->hi[1] - h->lo[1]) / c));
+        h->nrz = std::max(1, (int)ceil((h->hi[2] - h->lo[2]) / c));
+        if ((long long)h->nry * h->nrz * ESB_NCLASS <= cap) break;
         c *= 1.05;
     }
-    const double cell = c;
     h->cell_edge = c;
+    // cubes of the quad order: table (2 B per (class, cube)) + one u16 index array in the same scratch
+    const int capq = 5 * h->n_pad - 16;
+    double qc = h->quad_edge;
+    for (;;) {
+        h->qcx = std::max(1, (int)ceil((h->hi[0] - h->lo[0]) / qc));
+        h->qcy = std::max(1, (int)ceil((h->hi[1] - h->lo[1]) / qc));
+        h->qcz = std::max(1, (int)ceil((h->hi[2] - h->lo[2]) / qc));
+        if ((long long)h->qcx * h->qcy * h->qcz * ESB_NCLASS <= capq) break;
+        qc *= 1.05;
+    }
+    h->quad_edge = qc;
 
     const int nt = (int)h->tables.size();
     std::vector<DevTab> closed(nt), arr(nt);
@@ -212,15 +228,14 @@ int rebuild_setups(esb_handle *h)
     memset(setups.data(), 0, sizeof(PairSetup) * ESB_N_SETUPS);
     auto fill = [&](PairSetup &ps, auto cut_of, auto tab_of) {
         for (int a = 1; a <= h->n_types; a++) {
-            double cmax = 0.0;
             for (int b = 1; b <= h->n_types; b++) {
                 const double cu = cut_of(a, b);
                 const int q = a * ESB_MAXT + b;
                 ps.tabid[q] = (unsigned char)tab_of(a, b);
-                cmax = std::max(cmax, cu);
                 ps.cutsq_skin[q] = (float)((cu + h->skin) * (cu + h->skin));
+                float &reach = ps.reach[a * 8 + k_class_of[b]];
+                if (cu > 0.0) reach = std::max(reach, (float)((cu + h->skin) * (1.0 + 1e-6) + 1e-6));
             }
-            ps.range[a] = (unsigned char)std::max(1, (int)ceil((cmax + h->skin) / cell));
         }
     };
     if (h->have_soft) {
@@ -261,8 +276,9 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     k.ramp_bond[1][0] = 0.033; k.ramp_bond[1][1] = 1.0;   // variable chromatinr0 equal ramp(0.033,1.0)  (:635)
     k.ramp_bond[2][0] = 0.033; k.ramp_bond[2][1] = 0.3;   // variable actinr0 equal ramp(0.033,0.3)      (:638)
     k.ramp_soft[0] = 0.0; k.ramp_soft[1] = 60.0;          // variable prefactor equal ramp(0,60)         (:627)
-    k.ncx = h->ncx; k.ncy = h->ncy; k.ncz = h->ncz; k.ncells = h->ncx * h->ncy * h->ncz;
-    k.cell_inv = (float)(1.0 / h->cell_edge);
+    k.nry = h->nry; k.nrz = h->nrz; k.nrows = h->nry * h->nrz;
+    k.row_inv = (float)(1.0 / h->cell_edge);
+    k.qcx = h->qcx; k.qcy = h->qcy; k.qcz = h->qcz; k.qcell_inv = (float)(1.0 / h->quad_edge);
     k.pos4 = h->d_pos4; k.vel4 = h->d_vel4; k.rs = h->d_rs; k.frozen = h->d_frozen;
     k.bterm = h->d_bterm; k.spec = h->d_spec; k.n_topo_pad = h->n_topo_pad;
     k.setups = h->d_setups;
@@ -270,10 +286,7 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     k.n_tables = (int)h->tables.size();
     k.tabval = h->d_tabval; k.tabe = h->d_tabe; k.tlm1 = h->tlm1;
     k.nl_pool = h->d_nl_pool; k.nl_qinfo = h->d_nl_qinfo;
-    {   // species classes (run_single_shoebox.py:23-33): chromatin-like {1,2,6,7,9,10,11}, actin 3, RBP 4, RNP 5, Ser5P 8
-        static const unsigned char cls[ESB_MAXT] = {0, 0, 0, 1, 2, 3, 0, 0, 4, 0, 0, 0};
-        memcpy(k.class_of, cls, ESB_MAXT);
-    }
+    memcpy(k.class_of, k_class_of, ESB_MAXT);
     k.descs = h->d_descs;
     k.lay = h->lay; k.enh_idx = h->d_enh; k.s5p_idx = h->d_s5p; k.cluster_r = h->d_cluster_r;
     k.frames = h->d_frames; k.rawd = h->d_rawd; k.hist = h->d_hist; k.max_chunks = h->n_chunks;
@@ -314,6 +327,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     h->n_pad = (n_atoms + 31) & ~31;
     if (const char *s = getenv("ESB_SKIN")) h->skin = atof(s);
     if (const char *s = getenv("ESB_CELL")) h->cell_edge = atof(s);
+    if (const char *s = getenv("ESB_QCELL")) h->quad_edge = atof(s);
     memset(h->soft_cut, 0, sizeof(h->soft_cut));
     memset(h->maps, 0, sizeof(h->maps));
     h->frozen.assign(h->n_pad, 0);

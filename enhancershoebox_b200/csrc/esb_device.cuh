@@ -10,13 +10,13 @@
 #include "../../include/esb.h"
 
 #ifndef ESB_THREADS
-#define ESB_THREADS 256
+#define ESB_THREADS 512
 #endif
 #ifndef ESB_PREFETCH
 #define ESB_PREFETCH 4                  // neighbour-list entries each lane keeps in flight (even)
 #endif
 #ifndef ESB_MIN_CTAS
-#define ESB_MIN_CTAS 3                  // resident CTAs per SM the step kernel is compiled for
+#define ESB_MIN_CTAS 2                  // resident CTAs per SM the step kernel is compiled for (2 x 16 warps: 64 registers)
 #endif
 #define ESB_G 8                      // lanes cooperating on one atom (pair loop and list build)
 #define ESB_GROUPS (ESB_THREADS / ESB_G)
@@ -24,7 +24,7 @@
 #define ESB_MAX_SPEC 8               // excluded partners per atom (linear chain: 6)
 #define ESB_NL_MAXNB 1023            // neighbours per atom (12-bit count in the head word)
 #define ESB_NL_STRIDE 1024           // list arena per bead (entries); LAMMPS: neigh_modify one 10000
-#define ESB_NCLASS 5                 // species classes for the slot sort: chromatin-like, actin, RBP, RNP, Ser5P
+#define ESB_NCLASS 6                 // species classes for the row sort: chromatin-like, actin, RBP, RNP, Ser5P, gene body (induced/active)
 #define ESB_N_COUNTERS 10             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases
 #define ESB_N_SETUPS 9               // 0 = pair soft, 1..4 = table maps 0..3 (closed form + patch), 5..8 = same maps, array lookups
 
@@ -51,7 +51,7 @@ struct PairSetup {
     float cutsq[ESB_MAXT * ESB_MAXT];       // accept test (soft: rc^2; table: effective cut^2)
     float cutsq_skin[ESB_MAXT * ESB_MAXT];  // list test (cut+skin)^2
     unsigned char tabid[ESB_MAXT * ESB_MAXT];
-    unsigned char range[ESB_MAXT + 4];      // cells to search on each side, per type of the central atom
+    float reach[ESB_MAXT * 8];              // [type][class]: largest cut+skin towards any type of that class (0: none)
 };
 
 struct Layout {
@@ -80,9 +80,12 @@ struct KArgs {
     float bond_k[3], angle_k[3];
     double ramp_bond[3][2];   // ramp(v0,v1) of fix s2/s3 per bond type
     double ramp_soft[2];
-    // cell grid
-    int ncx, ncy, ncz, ncells;
-    float cell_inv;           // 1 / cell edge
+    // row grid of the list build: rows of edge 1/row_inv over (y, z), full length in x
+    int nry, nrz, nrows;
+    float row_inv;
+    // cubes that group the beads into quads (build order)
+    int qcx, qcy, qcz;
+    float qcell_inv;
     // device arrays
     float4 *pos4;             // [R][n_pad] x,y,z,type bits
     float4 *vel4;             // [R][n_pad]

@@ -27,10 +27,12 @@ struct Smem {
     double *dmisc;
     // aliases into the force region, valid only inside build_lists()
     unsigned short *cend;        // [nslots + 2]  running end offset of every slot
-    unsigned short *sidx;        // [n_pad]       atom indices sorted by slot
+    unsigned short *sidx;        // [n_pad]       atom indices sorted by (slot, x); a second [n_pad] block behind it is sort scratch
+    float *xs;                   // [n_pad]       x of the sorted beads
+    unsigned short *qord;        // [n_pad]       quad order of the build (own region: it outlives the scratch reuse)
 };
 
-enum { M_POOLCUR = 0, M_FAIL, M_PAIRS, M_CURLIST, M_SCAN /* one per warp */,
+enum { M_QCTR = 0 /* next quad of the running build / force loop */, M_FAIL, M_PAIRS, M_CURLIST, M_SCAN /* one per warp */,
        M_CNT_PROM = M_SCAN + ESB_THREADS / 32, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */, M_END = M_HIST + 52 };
 static_assert((ESB_NL_MAXNB + 1) % ESB_THREADS == 0, "length-sort scan: equal share of counters per thread");
 enum { D_RR = 0, D_PROBE = 3, D_GENE = 6, D_END = 10 };
@@ -42,8 +44,9 @@ __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables)
     b += (size_t)n_pad * 4 * 9;              // v, f, xbuild
     b += (sizeof(PairSetup) + 15) & ~(size_t)15;
     b += ((size_t)n_tables * sizeof(DevTab) + 15) & ~(size_t)15;
-    b += (size_t)M_END * 4;
+    b += ((size_t)M_END * 4 + 15) & ~(size_t)15;
     b += (size_t)D_END * 8;
+    b += (size_t)n_pad * 2;                  // quad order
     return (b + 15) & ~(size_t)15;
 }
 
@@ -69,9 +72,11 @@ __device__ __forceinline__ Smem carve(const KArgs &a)
     S.setup = reinterpret_cast<PairSetup *>(base + o); o += (sizeof(PairSetup) + 15) & ~(size_t)15;
     S.tab = reinterpret_cast<DevTab *>(base + o); o += ((size_t)a.n_tables * sizeof(DevTab) + 15) & ~(size_t)15;
     S.dmisc = reinterpret_cast<double *>(base + o); o += (size_t)D_END * 8;
-    S.misc = reinterpret_cast<int *>(base + o);
+    S.misc = reinterpret_cast<int *>(base + o); o += ((size_t)M_END * 4 + 15) & ~(size_t)15;
+    S.qord = reinterpret_cast<unsigned short *>(base + o);
     S.cend = reinterpret_cast<unsigned short *>(S.fx);
-    S.sidx = S.cend + ((a.ncells * ESB_NCLASS + 2 + 7) & ~7);
+    S.sidx = S.cend + ((a.nrows * ESB_NCLASS + 2 + 7) & ~7);
+    S.xs = reinterpret_cast<float *>(S.sidx + 2 * np);
     return S;
 }
 
@@ -86,6 +91,20 @@ __device__ __forceinline__ float rcp_approx(const float x)
 // Shared memory viewed as float4 words: indexing this array (instead of dereferencing pointers
 // carried in a struct) lets the compiler emit LDS [reg + immediate] in the hot loops.
 extern __shared__ __align__(16) float4 smem4[];
+// The hot loops address shared memory through a 32-bit base held in a register and ld.shared: the compiler's
+// own addressing of smem4[] re-derives the CTA's shared window (S2UR CgaCtaId, ULEA ...) at every use.
+__device__ __forceinline__ unsigned int smem_base()
+{
+    unsigned int b = (unsigned int)__cvta_generic_to_shared(smem_raw);
+    asm volatile("mov.u32 %0, %0;" : "+r"(b));        // opaque: kept in a register, not rematerialised
+    return b;
+}
+__device__ __forceinline__ float4 lds128(const unsigned int addr)
+{
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 template <int NP>
 __device__ __forceinline__ int tab_off4(const KArgs &a)
 {
@@ -99,43 +118,29 @@ __device__ __forceinline__ int cell_coord(float x, float lo, float inv, int n)
     return min(max(c, 0), n - 1);
 }
 
+// slot of a bead in the row sort: (species class, z row, y row), class-major
 __device__ __forceinline__ int slot_of(const KArgs &a, const float4 p)
 {
-    const int cx = cell_coord(p.x, a.lo[0], a.cell_inv, a.ncx);
-    const int cy = cell_coord(p.y, a.lo[1], a.cell_inv, a.ncy);
-    const int cz = cell_coord(p.z, a.lo[2], a.cell_inv, a.ncz);
-    return ((cz * a.ncy + cy) * a.ncx + cx) * ESB_NCLASS + a.class_of[__float_as_int(p.w) & 0xff];
+    const int ry = cell_coord(p.y, a.lo[1], a.row_inv, a.nry);
+    const int rz = cell_coord(p.z, a.lo[2], a.row_inv, a.nrz);
+    return a.class_of[__float_as_int(p.w) & 0xff] * a.nrows + rz * a.nry + ry;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Neighbour list build.  Stands in for LAMMPS' binned neighbour build (`neighbor 0.3 multi`,
-// `neigh_modify every 1 delay 10 check yes`, run_single_shoebox.py:532-533): per-type-pair
-// cutoff + skin, 1-2/1-3/1-4 partners excluded (default special_bonds).  Full list (both i->j and
-// j->i) so the force loop needs no scatter; every entry carries the pair's table id.
-//
-// Beads are counting-sorted into slots = (cell, species class); inside a slot they are ordered by
-// atom index, so every bead's list is deterministic.  The build walks the slot order four beads
-// ("quad": same cell, same class, hence near-identical candidate ranges) per warp, one per group of
-// ESB_G lanes, in lock step.  Afterwards the descriptors are re-sorted by list length: that is the
-// order in which the force loop forms its quads, so that the four lists of a quad end together.
-// ------------------------------------------------------------------------------------------------
-template <int NP>
-__device__ __noinline__ void build_lists(const KArgs &a, const int r)
+// Counting sort of the beads into `nslots` slots (CTA-wide; called by all threads).  Afterwards S.cend[s] is
+// the END offset of slot s (start = S.cend[s-1], 0 for s = 0) and `tmp` holds the bead indices grouped by slot,
+// in arbitrary order inside a slot.  The counters are u16 packed in pairs for the shared-memory atomics.
+template <class SlotFn>
+__device__ __forceinline__ void slot_sort(const Smem &S, const KArgs &a, const int nslots, unsigned short *tmp, SlotFn slot_fn)
 {
-    const Smem S = carve<NP>(a);
     const int tid = threadIdx.x, n = a.n_atoms;
     const int lane = tid & 31, warp = tid >> 5;
-    const int nslots = a.ncells * ESB_NCLASS;
     unsigned int *cw = reinterpret_cast<unsigned int *>(S.cend);
     const int ncw = (nslots + 2 + 1) >> 1;
     for (int w = tid; w < ncw; w += ESB_THREADS) cw[w] = 0u;
-    if (tid == 0) S.misc[M_CURLIST] = 0;
     __syncthreads();
     // count (slot s is stored at position s+1 so that, after the scan, position s holds start(s))
     for (int i = tid; i < n; i += ESB_THREADS) {
-        const float4 p = S.pos[i];
-        S.bx[i] = p.x; S.by[i] = p.y; S.bz[i] = p.z;
-        const int slot = slot_of(a, p) + 1;
+        const int slot = slot_fn(S.pos[i]) + 1;
         atomicAdd(&cw[slot >> 1], 1u << (16 * (slot & 1)));
     }
     __syncthreads();
@@ -159,117 +164,241 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         for (int c = b0; c < b1; c++) { base += S.cend[c]; S.cend[c] = (unsigned short)base; }
     }
     __syncthreads();
-    // scatter: cend[s] (= start of s) is the cursor of slot s; afterwards cend[s] = end of s.  The order
-    // inside a slot is whatever the atomics produced; `tmp` holds it until the rank sort below.
-    unsigned short *tmp = S.sidx + a.n_pad;
+    // scatter: cend[s] (= start of s) is the cursor of slot s; afterwards cend[s] = end of s
     for (int i = tid; i < n; i += ESB_THREADS) {
-        const int slot = slot_of(a, S.pos[i]);
+        const int slot = slot_fn(S.pos[i]);
         const unsigned int old = atomicAdd(&cw[slot >> 1], 1u << (16 * (slot & 1)));
         tmp[(old >> (16 * (slot & 1))) & 0xffffu] = (unsigned short)i;
     }
     __syncthreads();
-    // order every slot by atom index (deterministic lists): one thread per bead counts the beads of its
-    // slot with a smaller index -- O(sum n_s^2) comparisons spread over the CTA instead of one thread
-    // insertion-sorting the 100+ beads of a dense slot while the others wait
-    for (int i = tid; i < n; i += ESB_THREADS) {
-        const int slot = slot_of(a, S.pos[i]);
-        const int s0 = slot ? S.cend[slot - 1] : 0, s1 = S.cend[slot];
-        int rank = 0;
-        for (int p = s0; p < s1; p++) rank += (tmp[p] < (unsigned short)i);
-        S.sidx[s0 + rank] = (unsigned short)i;
-    }
-    __syncthreads();
+}
 
-    // ---- candidate tests: one quad (4 consecutive beads of the slot order: same cell and class, hence
-    // the same candidate rows) per warp; every lane takes one candidate j and tests it against all
-    // four beads, so a warp iteration performs 128 distance tests for two shared-memory loads.
-    // Accepted (bead, j) pairs are compacted per bead with a ballot; bead i owns the fixed arena
-    // [i * ESB_NL_STRIDE, (i+1) * ESB_NL_STRIDE) of the replica's pool.
+// ------------------------------------------------------------------------------------------------
+// Neighbour list build.  Stands in for LAMMPS' binned neighbour build (`neighbor 0.3 multi`,
+// `neigh_modify every 1 delay 10 check yes`, run_single_shoebox.py:532-533): per-type-pair
+// cutoff + skin, 1-2/1-3/1-4 partners excluded (default special_bonds).  Full list (both i->j and
+// j->i) so the force loop needs no scatter; every entry carries the pair's table id.
+//
+// Beads are counting-sorted into slots = (species class, row), a row being a (y, z) column of edge
+// ~1.2 that spans the box in x, and ordered by x inside a slot.  The candidates of a bead towards
+// class B are then, for every row within reach(type, B) in y and z, ONE contiguous span of the sorted
+// order: the beads of that row with x within reach -- found by binary search, at full resolution in x
+// and with the cutoff of that class pair (0.7 for RBP-RBP ... 3.2 for RNP-RNP) instead of the
+// largest cutoff of the bead.  The build walks the sorted order four beads ("quad": same class,
+// same or adjacent row, adjacent in x) per warp: the lanes first resolve the quad's spans (one span
+// per lane), then run through the concatenation of the spans 32 candidates at a time; every lane
+// tests its candidate against all four beads (128 distance tests per iteration) and accepted
+// (bead, j) pairs are ballot-compacted into the bead's arena.  Lists are deterministic (the sorted
+// order is a function of the positions only).  Afterwards the descriptors are re-sorted by list
+// length: that is the order in which the force loop forms its quads.
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__device__ __noinline__ void build_lists(const KArgs &a, const int r)
+{
+    const Smem S = carve<NP>(a);
+    const int tid = threadIdx.x, n = a.n_atoms;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nrows = a.nrows, nry = a.nry, nrz = a.nrz;
+    const int nslots = nrows * ESB_NCLASS;
+    if (tid == 0) { S.misc[M_CURLIST] = 0; S.misc[M_QCTR] = 0; }
+    // ---- (A) quad order: beads grouped by (class, cube of edge ~2.2), by atom index inside a group.  Four
+    //      consecutive beads of this order form a quad: same species, close together, hence a small bounding box.
+    {
+        const int nq_slots = a.qcx * a.qcy * a.qcz * ESB_NCLASS;
+        unsigned short *tmp = S.cend + ((nq_slots + 2 + 7) & ~7);
+        auto cube_of = [&](const float4 p) {
+            const int cx = cell_coord(p.x, a.lo[0], a.qcell_inv, a.qcx);
+            const int cy = cell_coord(p.y, a.lo[1], a.qcell_inv, a.qcy);
+            const int cz = cell_coord(p.z, a.lo[2], a.qcell_inv, a.qcz);
+            return ((a.class_of[__float_as_int(p.w) & 0xff] * a.qcz + cz) * a.qcy + cy) * a.qcx + cx;
+        };
+        slot_sort(S, a, nq_slots, tmp, cube_of);
+        for (int i = tid; i < n; i += ESB_THREADS) {
+            const int slot = cube_of(S.pos[i]);
+            const int s0 = slot ? S.cend[slot - 1] : 0, s1 = S.cend[slot];
+            int rank = 0;
+            for (int q = s0; q < s1; q++) rank += (tmp[q] < (unsigned short)i);
+            S.qord[s0 + rank] = (unsigned short)i;
+        }
+        __syncthreads();
+    }
+    // ---- (B) candidate order: beads grouped by (class, row), by (x, atom index) inside a row ----
+    {
+        unsigned short *tmp = S.sidx + a.n_pad;
+        auto row_of = [&](const float4 p) { return slot_of(a, p); };
+        slot_sort(S, a, nslots, tmp, row_of);
+        for (int i = tid; i < n; i += ESB_THREADS) {
+            const float4 p = S.pos[i];
+            S.bx[i] = p.x; S.by[i] = p.y; S.bz[i] = p.z;
+            const int slot = slot_of(a, p);
+            const int s0 = slot ? S.cend[slot - 1] : 0, s1 = S.cend[slot];
+            int rank = 0;
+            for (int q = s0; q < s1; q++) {
+                const int o = tmp[q];
+                const float xo = S.pos[o].x;
+                rank += (xo < p.x) || (xo == p.x && o < i);
+            }
+            S.sidx[s0 + rank] = (unsigned short)i;
+            S.xs[s0 + rank] = p.x;
+        }
+        __syncthreads();
+    }
+
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lt_mask = (1u << lane) - 1u;
     unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESB_NL_STRIDE;
-    uint2 *qbuild = a.nl_qinfo + ((size_t)r * 2 + 1) * a.n_pad;     // descriptors in build (slot) order
-    const float lox = a.lo[0], loy = a.lo[1], loz = a.lo[2], cinv = a.cell_inv;
-    const int ncx = a.ncx, ncy = a.ncy, ncz = a.ncz, n_topo = a.n_topo;
+    uint2 *qbuild = a.nl_qinfo + ((size_t)r * 2 + 1) * a.n_pad;     // descriptors in build (sorted) order
+    const float loy = a.lo[1], loz = a.lo[2], rinv = a.row_inv;
+    const int n_topo = a.n_topo;
     unsigned int listed = 0;
     const int nquads = (n + 3) >> 2;
-    for (int q = warp; q < nquads; q += ESB_THREADS / 32) {
+    for (;;) {
+        // quads are handed out dynamically: their cost varies by two orders of magnitude with the species
+        int q = 0;
+        if (lane == 0) q = atomicAdd(&S.misc[M_QCTR], 1);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= nquads) break;
         int ia[4], ta[4], cnt[4];
         float4 pa[4];
-        int x0 = ncx, x1 = -1, y0 = ncy, y1 = -1, z0 = ncz, z1 = -1;
+        float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f, zmin = 3.0e38f, zmax = -3.0e38f;
         bool any_topo = false;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int idx = min(4 * q + b, n - 1);               // the last quad may repeat its last bead
-            ia[b] = S.sidx[idx];
+            ia[b] = S.qord[idx];
             pa[b] = S.pos[ia[b]];
             ta[b] = __float_as_int(pa[b].w) & 0xff;
             cnt[b] = 0;
-            const int rng = S.setup->range[ta[b]];
-            const int cx = cell_coord(pa[b].x, lox, cinv, ncx), cy = cell_coord(pa[b].y, loy, cinv, ncy), cz = cell_coord(pa[b].z, loz, cinv, ncz);
-            x0 = min(x0, max(cx - rng, 0)); x1 = max(x1, min(cx + rng, ncx - 1));
-            y0 = min(y0, max(cy - rng, 0)); y1 = max(y1, min(cy + rng, ncy - 1));
-            z0 = min(z0, max(cz - rng, 0)); z1 = max(z1, min(cz + rng, ncz - 1));
+            xmin = fminf(xmin, pa[b].x); xmax = fmaxf(xmax, pa[b].x);
+            ymin = fminf(ymin, pa[b].y); ymax = fmaxf(ymax, pa[b].y);
+            zmin = fminf(zmin, pa[b].z); zmax = fmaxf(zmax, pa[b].z);
             any_topo |= ia[b] < n_topo;
         }
+        // spans of the quad: for class B every row within reach of the quad's bounding box; the span list is the
+        // concatenation over the classes.  Lane B < ESB_NCLASS works out and keeps the numbers of class B:
+        // my_pack = first y row | rows in y << 8 | first z row << 16, spans [my_cum, my_end), reach.
+        int my_pack = 0, my_end = 0, my_cum = 0;
+        float my_reach = 0.0f;
+        {
+            int nsp = 0;
+            if (lane < ESB_NCLASS) {
+                const float *rc = S.setup->reach + lane;
+                const float c = fmaxf(fmaxf(rc[ta[0] * 8], rc[ta[1] * 8]), fmaxf(rc[ta[2] * 8], rc[ta[3] * 8]));
+                const int first = lane * nrows;
+                const int pop = (int)S.cend[first + nrows - 1] - (first ? (int)S.cend[first - 1] : 0);
+                if (c > 0.0f && pop > 0) {
+                    const int y0 = cell_coord(ymin - c, loy, rinv, nry), y1 = cell_coord(ymax + c, loy, rinv, nry);
+                    const int z0 = cell_coord(zmin - c, loz, rinv, nrz), z1 = cell_coord(zmax + c, loz, rinv, nrz);
+                    my_pack = y0 | ((y1 - y0 + 1) << 8) | (z0 << 16);
+                    my_reach = c;
+                    nsp = (y1 - y0 + 1) * (z1 - z0 + 1);
+                }
+            }
+            my_end = nsp;
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const int t = __shfl_up_sync(FULL, my_end, d);
+                if (lane >= d) my_end += t;
+            }
+            my_cum = my_end - nsp;
+        }
+        const int n_spans = __shfl_sync(FULL, my_end, ESB_NCLASS - 1);
         // Two warp-uniform specialisations keep the common inner loop short: `uniform` = the four beads
         // have the same type (one cutoff / table-id row per candidate), `any_topo` = some bead of the quad
         // is bonded (only then can a candidate be an excluded 1-2/1-3/1-4 partner).
         const bool uniform = (ta[0] == ta[1]) && (ta[1] == ta[2]) && (ta[2] == ta[3]);
-        unsigned int *outp[4];
-#pragma unroll
-        for (int b = 0; b < 4; b++) outp[b] = pool + (size_t)ia[b] * ESB_NL_STRIDE;
         const float *cs_row = S.setup->cutsq_skin;
         const unsigned char *tab_row = S.setup->tabid;
-        auto scan_rows = [&](auto topo_tag, auto uniform_tag) {
+        auto scan_spans = [&](auto topo_tag, auto uniform_tag) {
             constexpr bool TOPO = decltype(topo_tag)::value, UNIFORM = decltype(uniform_tag)::value;
-            for (int zz = z0; zz <= z1; zz++)
-                for (int yy = y0; yy <= y1; yy++) {
-                    const int row = (zz * ncy + yy) * ncx;
-                    const int s_first = (row + x0) * ESB_NCLASS;
-                    const int ka = s_first ? S.cend[s_first - 1] : 0;
-                    const int kb = S.cend[(row + x1) * ESB_NCLASS + ESB_NCLASS - 1];
-                    for (int k0 = ka; k0 < kb; k0 += 32) {
-                        const int k = k0 + lane;
-                        const bool live = k < kb;
-                        const int j = live ? S.sidx[k] : 0;
-                        const float4 pj = S.pos[j];
-                        const int tj = __float_as_int(pj.w) & 0xff;
-                        float cs_u = 0.0f;
-                        unsigned int ent_u = 0u;
-                        if (UNIFORM) {
-                            cs_u = cs_row[ta[0] * ESB_MAXT + tj];
-                            ent_u = (unsigned int)j | ((unsigned int)tab_row[ta[0] * ESB_MAXT + tj] << 16);
-                        }
+            for (int sp0 = 0; sp0 < n_spans; sp0 += 32) {
+                // ---- this lane's span: (class, row) -> slot -> the beads with x within reach ----
+                const int sp = sp0 + lane;
+                int B = 0;
 #pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            const float dx = pa[b].x - pj.x, dy = pa[b].y - pj.y, dz = pa[b].z - pj.z;
-                            const float r2 = dx * dx + dy * dy + dz * dz;
-                            const float cs = UNIFORM ? cs_u : cs_row[ta[b] * ESB_MAXT + tj];
-                            bool ok = live && (r2 < cs) && (j != ia[b]);
-                            if (TOPO) {
-                                if (ok && j < n_topo && ia[b] < n_topo) {
-                                    const uint4 sp = *reinterpret_cast<const uint4 *>(a.spec + (size_t)ia[b] * ESB_MAX_SPEC);
-                                    const unsigned int jj = (unsigned int)j;
-                                    ok = !((sp.x & 0xffffu) == jj || (sp.x >> 16) == jj || (sp.y & 0xffffu) == jj || (sp.y >> 16) == jj ||
-                                           (sp.z & 0xffffu) == jj || (sp.z >> 16) == jj || (sp.w & 0xffffu) == jj || (sp.w >> 16) == jj);
-                                }
+                for (int c = 0; c < ESB_NCLASS; c++) B += (sp >= __shfl_sync(FULL, my_end, c));
+                const int pack = __shfl_sync(FULL, my_pack, B & 7), cumB = __shfl_sync(FULL, my_cum, B & 7);
+                const float reach = __shfl_sync(FULL, my_reach, B & 7);
+                int slot = -1;
+                if (B < ESB_NCLASS) {
+                    const int li = sp - cumB, ny = (pack >> 8) & 0xff;
+                    const int dz = (int)(((float)li + 0.5f) * rcp_approx((float)ny));
+                    const int dy = li - dz * ny;
+                    slot = B * nrows + ((pack >> 16) + dz) * nry + (pack & 0xff) + dy;
+                }
+                const float xlo = xmin - reach, xhi = xmax + reach;
+                int ka = 0, kb = 0;
+                if (slot >= 0) { ka = slot ? (int)S.cend[slot - 1] : 0; kb = (int)S.cend[slot]; }
+                {   // first bead with x >= xlo, then first bead with x > xhi
+                    int lo_ = ka, hi_ = kb;
+                    while (__any_sync(FULL, lo_ < hi_)) {
+                        if (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (S.xs[mid] < xlo) lo_ = mid + 1; else hi_ = mid; }
+                    }
+                    ka = lo_;
+                    hi_ = kb;
+                    while (__any_sync(FULL, lo_ < hi_)) {
+                        if (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (S.xs[mid] <= xhi) lo_ = mid + 1; else hi_ = mid; }
+                    }
+                    kb = lo_;
+                }
+                const int len = kb - ka;
+                int incl = len;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                const int shift = ka - (incl - len);                 // candidate f of this span sits at sorted position f + shift
+                // ---- the concatenated spans, 32 candidates per iteration ----
+                for (int f0 = 0; f0 < total; f0 += 32) {
+                    const int f = f0 + lane;
+                    const bool live = f < total;
+                    int p = 0;                                       // span of candidate f: the first lane with incl > f
+#pragma unroll
+                    for (int st = 16; st >= 1; st >>= 1) {
+                        const int t = __shfl_sync(FULL, incl, p + st - 1);
+                        if (t <= f) p += st;
+                    }
+                    const int k = f + __shfl_sync(FULL, shift, p & 31);
+                    const int j = live ? S.sidx[k] : 0;
+                    const float4 pj = S.pos[j];
+                    const int tj = __float_as_int(pj.w) & 0xff;
+                    float cs_u = 0.0f;
+                    unsigned int ent_u = 0u;
+                    if (UNIFORM) {
+                        cs_u = cs_row[ta[0] * ESB_MAXT + tj];
+                        ent_u = (unsigned int)j | ((unsigned int)tab_row[ta[0] * ESB_MAXT + tj] << 16);
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const float dx = pa[b].x - pj.x, dy = pa[b].y - pj.y, dz = pa[b].z - pj.z;
+                        const float r2 = dx * dx + dy * dy + dz * dz;
+                        const float cs = UNIFORM ? cs_u : cs_row[ta[b] * ESB_MAXT + tj];
+                        bool ok = live && (r2 < cs) && (j != ia[b]);
+                        if (TOPO) {
+                            if (ok && j < n_topo && ia[b] < n_topo) {
+                                const uint4 sp4 = *reinterpret_cast<const uint4 *>(a.spec + (size_t)ia[b] * ESB_MAX_SPEC);
+                                const unsigned int jj = (unsigned int)j;
+                                ok = !((sp4.x & 0xffffu) == jj || (sp4.x >> 16) == jj || (sp4.y & 0xffffu) == jj || (sp4.y >> 16) == jj ||
+                                       (sp4.z & 0xffffu) == jj || (sp4.z >> 16) == jj || (sp4.w & 0xffffu) == jj || (sp4.w >> 16) == jj);
                             }
-                            const unsigned int bits = __ballot_sync(FULL, ok);
-                            if (ok) {
-                                const int slot = cnt[b] + __popc(bits & lt_mask);
-                                if (slot < ESB_NL_MAXNB)
-                                    outp[b][slot] = UNIFORM ? ent_u : ((unsigned int)j | ((unsigned int)tab_row[ta[b] * ESB_MAXT + tj] << 16));
-                            }
+                        }
+                        const unsigned int bits = __ballot_sync(FULL, ok);
+                        if (bits) {                                  // warp-uniform: most candidates are rejected by every bead
+                            const int at = cnt[b] + __popc(bits & lt_mask);
+                            if (ok && at < ESB_NL_MAXNB)
+                                pool[(unsigned int)ia[b] * ESB_NL_STRIDE + at] = UNIFORM ? ent_u : ((unsigned int)j | ((unsigned int)tab_row[ta[b] * ESB_MAXT + tj] << 16));
                             cnt[b] += __popc(bits);
                         }
                     }
                 }
+            }
         };
         using T_ = std::true_type;
         using F_ = std::false_type;
-        if (any_topo) { if (uniform) scan_rows(T_{}, T_{}); else scan_rows(T_{}, F_{}); }
-        else { if (uniform) scan_rows(F_{}, T_{}); else scan_rows(F_{}, F_{}); }
+        if (any_topo) { if (uniform) scan_spans(T_{}, T_{}); else scan_spans(T_{}, F_{}); }
+        else { if (uniform) scan_spans(F_{}, T_{}); else scan_spans(F_{}, F_{}); }
         if (lane < 4) {
             const int idx = 4 * q + lane;
             int c = lane == 0 ? cnt[0] : lane == 1 ? cnt[1] : lane == 2 ? cnt[2] : cnt[3];
@@ -404,29 +533,34 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
     const int gl = lane & (ESB_G - 1), grp = lane / ESB_G;
     double e_pair = 0.0, e_bond = 0.0, e_angle = 0.0;
     bonded_forces<ENERGY>(S, a, r0_1, r0_2, e_bond, e_angle);
+    if (tid == 0) S.misc[M_QCTR] = 0;
     __syncthreads();
     const unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESB_NL_STRIDE;
     const uint2 *qinfo = a.nl_qinfo + (size_t)r * 2 * a.n_pad;
-    const int toff4 = tab_off4<NP>(a);
+    const unsigned int sb = smem_base(), tbase = sb + 16u * (unsigned int)tab_off4<NP>(a);
     const float *tabval = a.tabval;
     const int tlm1 = a.tlm1;
     unsigned int npairs = 0;
-    // quads in order of decreasing list length, dealt round-robin to the warps; the next quad's
-    // descriptor is fetched (L2) while the current one is processed
+    // quads in order of decreasing list length, handed out dynamically (longest first: the warps finish
+    // together); the next quad's descriptor is fetched (L2) while the current one is processed
     const int nquads = (n + 3) >> 2;
-    const int warp = tid >> 5;
-    uint2 qi_next = make_uint2(0u, 0u);
-    if (warp < nquads && 4 * warp + grp < n) qi_next = qinfo[4 * warp + grp];
-    for (int q = warp; q < nquads; q += ESB_THREADS / 32) {
-        const uint2 qi = qi_next;
-        const int qn = q + ESB_THREADS / 32;
-        qi_next = make_uint2(0u, 0u);
+    auto next_quad = [&]() {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&S.misc[M_QCTR], 1);
+        return __shfl_sync(FULL, t, 0);
+    };
+    int q = next_quad();
+    uint2 qi = make_uint2(0u, 0u);
+    if (q < nquads && 4 * q + grp < n) qi = __ldcg(&qinfo[4 * q + grp]);
+    while (q < nquads) {
+        const int qn = next_quad();
+        uint2 qi_next = make_uint2(0u, 0u);
         if (qn < nquads && 4 * qn + grp < n) qi_next = __ldcg(&qinfo[4 * qn + grp]);
         const bool valid = 4 * q + grp < n;
         const int i = (int)(qi.y & 0xffffu);
         const int cnt = valid ? (int)(qi.y >> 16) : 0;
         const unsigned int *nl = pool + qi.x;
-        const float4 pi = smem4[i];
+        const float4 pi = lds128(sb + 16u * (unsigned int)i);
         const int cnt_max = __reduce_max_sync(FULL, cnt);
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
         // The list lives in L2/HBM: four loads per lane are kept in flight (entries e, e+G, e+2G, e+3G)
@@ -436,7 +570,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
         const unsigned int *lp = nl + gl;
         auto pair_body = [&](const unsigned int ent, const int e) {
             if (e < cnt) {
-                const float4 pj = smem4[ent & 0xffffu];
+                const float4 pj = lds128(sb + 16u * (ent & 0xffffu));
                 const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 const float r2 = dx * dx + dy * dy + dz * dz;
                 float fpair;
@@ -452,17 +586,18 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                     npairs++;
                 } else {
                     const unsigned int tb = ent >> 16;                          // table id of the pair (fixed between builds)
-                    const int T4 = toff4 + 3 * (int)tb;                               // DevTab = 3 float4 words
-                    const float4 t0 = smem4[T4];                                      // cutsq, invdelta_f, delta, innersq_f
+                    const unsigned int T4 = tbase + 48u * tb;                         // DevTab = 3 float4 words
+                    const float4 t0 = lds128(T4);                                     // cutsq, invdelta_f, delta, innersq_f
                     if (!(r2 < t0.x)) return;
-                    const float4 t1 = smem4[T4 + 1];                                  // K, is6, c, patch
+                    const float4 t1 = lds128(T4 + 16u);                               // K, is6, c, patch
                     const float u = (r2 - t0.w) * t0.y;
                     int it = (int)u;
                     const float frac = u - (float)it;
                     // |u - u_exact| <= 8 ulp-relative (dx: 1, squares+sums: 5, offset+scale: 2) = 4.8e-7 u
                     const float margin = fmaf(u, 5.0e-7f, 1.0e-4f);
                     if (!(frac > margin && frac < 1.0f - margin)) {
-                        const double2 t2 = *reinterpret_cast<const double2 *>(&smem4[T4 + 2]);
+                        const float4 t2f = lds128(T4 + 32u);
+                        const double2 t2 = make_double2(__hiloint2double(__float_as_int(t2f.y), __float_as_int(t2f.x)), __hiloint2double(__float_as_int(t2f.w), __float_as_int(t2f.z)));
                         const double innersq = t2.x, invdelta = t2.y;
                         const double ddx = __dsub_rn((double)pi.x, (double)pj.x), ddy = __dsub_rn((double)pi.y, (double)pj.y),
                                      ddz = __dsub_rn((double)pi.z, (double)pj.z);
@@ -476,8 +611,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                     const float qm = fmaf((float)it + 0.5f, t0.z, t0.w);
                     const float q2 = qm * qm;
                     const float x = fmaf(q2 * qm, t1.y, t1.z);
-                    float inv = rcp_approx(x);
-                    inv = inv * fmaf(-x, inv, 2.0f);
+                    const float inv = rcp_approx(x);                                // <= 1 ulp: 3 ulp on inv^3, far inside the 1e-5 parity bound
                     fpair = t1.x * q2 * (2.0f - x) * (inv * inv * inv);
                     if (!closed) fpair = tabval[tb * (unsigned int)tlm1 + it];   // predicated load: patch bins are rare
                     if (ENERGY) e_pair += 0.5 * (double)a.tabe[tb * (unsigned int)tlm1 + it];
@@ -507,6 +641,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
             fz += __shfl_xor_sync(FULL, fz, d);
         }
         if (valid && gl == 0) { S.fx[i] += fx; S.fy[i] += fy; S.fz[i] += fz; }
+        q = qn; qi = qi_next;
     }
     if (npairs) atomicAdd(&S.misc[M_PAIRS], (int)npairs);
     if (ENERGY) { energy[0] += e_pair; energy[1] += e_bond; energy[2] += e_angle; }

@@ -18,7 +18,7 @@ from . import ljsoft, protocol as P
 from .datafile import ShoeboxData
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libesb.so")
+LIB_PATH = os.environ.get("ESB_LIB") or os.path.join(_HERE, "libesb.so")   # ESB_LIB: perf experiments with a variant build
 MAXT = 12
 N_SHELL = 50
 FRAME_DOUBLES = 9

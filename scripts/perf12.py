@@ -1,0 +1,26 @@
+"""Phase breakdown on the bench workload (box 12, chunk-1000 frame) from the in-kernel cycle counters.
+usage: [ESB_LIB=variant.so] python scripts/perf12.py [R] [chunks] [tag]"""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from enhancershoebox_b200 import datafile, protocol as P, engine as E
+R = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+nch = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+tag = sys.argv[3] if len(sys.argv) > 3 else os.path.basename(os.environ.get("ESB_LIB", "libesb.so"))
+z = np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', 'snap_box12_chunk1000.npz'))
+d = datafile.make_shoebox(12, 3, False, seed=7)
+x = z['x1000'].astype(np.float64); v = z['v1000'].astype(np.float64); t = z['t1000'].astype(np.int32)
+eng = E.ShoeboxBatch(d, n_replicas=R, seeds=np.arange(R) + 1)
+eng.upload_state(x[None], v[None], t[None], replicate=True)
+plans = P.chunk_schedule('genes_stages', n_chunks=1000 + nch + 2)[1000:]
+eng.set_schedule(plans=plans, observe=True)
+eng.run(0, 2)
+eng.reset_counters()
+t0 = time.time(); eng.run(2, nch); dt = time.time() - t0
+c = eng.counters()
+ev = c['evals'].sum()
+tot = (c['cyc_atom'] + c['cyc_build'] + c['cyc_force'] + c['cyc_other']).mean()
+sh = {k: c[k].mean() / tot for k in ('cyc_atom', 'cyc_build', 'cyc_force', 'cyc_other')}
+print(f'{tag:28s} R={R} {nch*200*R/dt:.3e} rs/s  pairs/eval {c["pairs"].sum()/ev/2:.0f} listed/eval {c["listed"].sum()/ev/2:.0f} '
+      f'builds/chunk {c["builds"].mean()/nch:.1f} cyc/step {tot/(nch*200):.0f} atom {sh["cyc_atom"]:.3f} build {sh["cyc_build"]:.3f} '
+      f'(per build {c["cyc_build"].mean()/c["builds"].mean():.0f}) force {sh["cyc_force"]:.3f} ok {int((eng.status()==0).sum())}', flush=True)
