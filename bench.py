@@ -267,6 +267,7 @@ def run_native(args, w):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "replicas_per_gpu": R, "n_atoms": d.n_atoms, "md_steps_per_step": T_RUN,
                        "start_chunk": START_CHUNK, "l2": "state is SMEM-resident; neighbour arenas (R x 512 KiB) exceed L2",
+                       "neighbor": f"skin {P.NEIGH_SKIN} delay {P.NEIGH_DELAY} check yes (reference: run_single_shoebox.py:532-533)",
                        "parallelism": f"replicas sharded over {world} GPU(s), no collective on the step path"},
             "bead_steps_per_s": value * d.n_atoms,
             "e2e": {"value": e2e_value, "unit": "replica-steps/s", "h2d_bytes_per_step": int(2 * R * n_pad * 16),
@@ -278,6 +279,8 @@ def run_native(args, w):
                          "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({which} MEASURED_PEAKS.json); MEASURED_PEAKS has no FP32 entry",
                          "kernel": "esb_run_kernel", "launch_ms": ms, "steps_per_launch": K, "flop_per_replica_step": fl,
                          "pairs_in_cut_per_step": pairs_in_cut, "pairs_listed_per_step": listed,
+                         "list_builds_per_step": float(cnt["builds"].sum()) / max(float(cnt["steps"].sum()), 1.0),
+                         "dangerous_builds_per_step": float(cnt["dangerous"].sum()) / max(float(cnt["steps"].sum()), 1.0),
                          "phase_share": {k[4:]: v / cyc_tot for k, v in cyc.items()}},
             "clocks": sampler.summary(),
             "failed_replicas": int(fails[0]),

@@ -83,6 +83,7 @@ struct esb_handle {
     bool have_box = false, have_topo = false, have_soft = false, have_tables = false, have_layout = false, have_state = false;
     bool setups_dirty = true;
     double dt = 0.005, t_target = 1.0, t_damp = 0.5, wall_eps = 100.0, wall_cut = 3.0, skin = 0.3, cell_edge = 2.8, quad_edge = 2.2;
+    int neigh_delay = 10;
     int langevin_mode = 1;
     double bond_k[3] = {0, 90.0, 90.0}, bond_r0[3] = {0, 1.0, 0.3}, angle_k[3] = {0, 100.0 / 60.0, 33.0};
     double soft_cut[ESB_MAXT * ESB_MAXT];
@@ -272,6 +273,7 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     k.wall_eps = (float)h->wall_eps; k.wall_cut = (float)h->wall_cut;
     k.skin_half_sq = (float)(0.25 * h->skin * h->skin);
     k.langevin_mode = h->langevin_mode;
+    k.neigh_delay = h->neigh_delay;
     for (int t = 0; t < 3; t++) { k.bond_k[t] = (float)h->bond_k[t]; k.angle_k[t] = (float)h->angle_k[t]; }
     k.ramp_bond[1][0] = 0.033; k.ramp_bond[1][1] = 1.0;   // variable chromatinr0 equal ramp(0.033,1.0)  (:635)
     k.ramp_bond[2][0] = 0.033; k.ramp_bond[2][1] = 0.3;   // variable actinr0 equal ramp(0.033,0.3)      (:638)
@@ -326,6 +328,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     h->device = device; h->R = n_replicas; h->N = n_atoms; h->n_types = n_types;
     h->n_pad = (n_atoms + 31) & ~31;
     if (const char *s = getenv("ESB_SKIN")) h->skin = atof(s);
+    if (const char *s = getenv("ESB_DELAY")) h->neigh_delay = atoi(s);
     if (const char *s = getenv("ESB_CELL")) h->cell_edge = atof(s);
     if (const char *s = getenv("ESB_QCELL")) h->quad_edge = atof(s);
     memset(h->soft_cut, 0, sizeof(h->soft_cut));
@@ -476,6 +479,13 @@ int esb_set_fixes(esb_handle *h, double dt, double t_target, double t_damp, int 
         return fail(ESB_EINVAL, "bad fix parameters");
     h->dt = dt; h->t_target = t_target; h->t_damp = t_damp; h->langevin_mode = langevin_mode;
     h->wall_eps = wall_eps; h->wall_cut = wall_cut;
+    return ESB_OK;
+}
+
+int esb_set_neighbor(esb_handle *h, double skin, int delay)
+{
+    if (!h || !(skin > 0) || delay < 0) return fail(ESB_EINVAL, "bad neighbour parameters (skin %g, delay %d)", skin, delay);
+    h->skin = skin; h->neigh_delay = delay; h->setups_dirty = true;
     return ESB_OK;
 }
 

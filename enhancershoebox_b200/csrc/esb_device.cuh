@@ -25,7 +25,7 @@
 #define ESB_NL_MAXNB 1023            // neighbours per atom (12-bit count in the head word)
 #define ESB_NL_STRIDE 1024           // list arena per bead (entries); LAMMPS: neigh_modify one 10000
 #define ESB_NCLASS 6                 // species classes for the row sort: chromatin-like, actin, RBP, RNP, Ser5P, gene body (induced/active)
-#define ESB_N_COUNTERS 10             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases
+#define ESB_N_COUNTERS 11             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases, dangerous builds
 #define ESB_N_SETUPS 9               // 0 = pair soft, 1..4 = table maps 0..3 (closed form + patch), 5..8 = same maps, array lookups
 
 // One (KEY,cut) table, 48 bytes, read in the force loop as two float4 (+ two doubles on the rare
@@ -77,6 +77,7 @@ struct KArgs {
     float lo[3], hi[3];
     float dt, gamma1, gamma2, wall_eps, wall_cut, skin_half_sq;
     int langevin_mode;
+    int neigh_delay;          // neigh_modify delay N: no list build sooner than N steps after the last one
     float bond_k[3], angle_k[3];
     double ramp_bond[3][2];   // ramp(v0,v1) of fix s2/s3 per bond type
     double ramp_soft[2];

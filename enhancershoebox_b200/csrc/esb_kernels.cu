@@ -952,9 +952,14 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
         __syncthreads();
         ESB_TICK(t_obs)
-        int rebuild = 1;
+        // [LAMMPS-ext] Neighbor::decide with `neigh_modify every 1 delay 10 check yes` (run_single_shoebox.py:533):
+        // every run builds at set-up; afterwards a build needs `delay` steps since the last one AND a bead that
+        // moved further than skin/2.  A build already due at the first permitted step is a "dangerous build".
+        int rebuild = 1, ago = 0;
+        unsigned long long n_danger = 0;
+        const int delay = max(a.neigh_delay, 1);
         for (int it = 0; it <= d.n_steps; it++) {
-            if (rebuild) { build_lists<NP>(a, r); n_builds++; ESB_TICK(t_build) }
+            if (rebuild) { build_lists<NP>(a, r); n_builds++; if (ago == delay) n_danger++; ago = 0; ESB_TICK(t_build) }
             if (d.pair_mode == 1) force_phase<NP, 1, false>(a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
             else force_phase<NP, 2, false>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
             n_evals++;
@@ -965,6 +970,8 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             // integrate of the next one (it < n_steps).  __syncthreads_or only tells whether ANY thread
             // passed non-zero, so it carries the rebuild vote; failure bits travel through shared memory.
             rebuild = __syncthreads_or(atom_phase<NP>(a, it > 0, it < d.n_steps, k0, k1, rs.eval));
+            ago++;
+            rebuild = rebuild && (ago >= delay);
             rs.eval++;
             ESB_TICK(t_atom)
             failed = S.misc[M_FAIL];
@@ -997,6 +1004,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             cn[3] += n_listed;
             cn[4] += n_steps_done;
             cn[5] = (unsigned long long)rs.total_active;
+            cn[10] += n_danger;
         }
         __syncthreads();                         // every thread's state stores are issued ...
         if (tid == 0) { __threadfence(); atomicExch(&progress[r], lc + 1); }   // ... and published

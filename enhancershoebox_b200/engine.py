@@ -54,6 +54,7 @@ _SIGNATURES = {
     "esb_set_topology": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "esb_set_coeffs": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "esb_set_fixes": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]),
+    "esb_set_neighbor": (C.c_int, [C.c_void_p, C.c_double, C.c_int]),
     "esb_set_soft": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "esb_set_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                  C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ClosedForm)]),
@@ -162,7 +163,7 @@ class ShoeboxBatch:
 
     def __init__(self, data, n_replicas: int | None = None, driver: str = "genes_stages", condition: str = "Control",
                  device: int = 0, table_file: str | None = None, seeds=None, thresholds=None, activations=None,
-                 langevin_mode: int = 1):
+                 langevin_mode: int = 1, neigh_skin: float = P.NEIGH_SKIN, neigh_delay: int = P.NEIGH_DELAY):
         """`data`: one ShoeboxData (copied to all replicas) or a list with one per replica (same
         topology).  `thresholds` = -x values, `activations` = -a values (per mille, as on the CLI)."""
         self.lib = load_library()
@@ -191,6 +192,8 @@ class ShoeboxBatch:
         ak = np.array([0.0, P.ANGLE_K[1], P.ANGLE_K[2]])
         self._check(self.lib.esb_set_coeffs(self.h, _dp(bk), _dp(br), _dp(ak)))
         self._check(self.lib.esb_set_fixes(self.h, P.DT, P.LANGEVIN_T, P.LANGEVIN_DAMP, langevin_mode, P.WALL_EPS, P.WALL_CUT))
+        if "ESB_SKIN" not in os.environ and "ESB_DELAY" not in os.environ:          # (perf experiments override through the environment)
+            self._check(self.lib.esb_set_neighbor(self.h, float(neigh_skin), int(neigh_delay)))
         sc = np.ascontiguousarray(P.soft_cutoffs(), np.float64)
         self._check(self.lib.esb_set_soft(self.h, _dp(sc)))
         # pair tables
@@ -336,10 +339,10 @@ class ShoeboxBatch:
         return st
 
     def counters(self):
-        out = np.empty((self.R, 10), np.int64)
+        out = np.empty((self.R, 11), np.int64)
         self._check(self.lib.esb_get_counters(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
         return dict(evals=out[:, 0], builds=out[:, 1], pairs=out[:, 2], listed=out[:, 3], steps=out[:, 4], total_active=out[:, 5],
-                    cyc_atom=out[:, 6], cyc_build=out[:, 7], cyc_force=out[:, 8], cyc_other=out[:, 9])
+                    cyc_atom=out[:, 6], cyc_build=out[:, 7], cyc_force=out[:, 8], cyc_other=out[:, 9], dangerous=out[:, 10])
 
     def reset_counters(self):
         self._check(self.lib.esb_reset_counters(self.h))

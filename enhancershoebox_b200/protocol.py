@@ -36,6 +36,9 @@ SIG_CHROMATIN_NM = 60
 POL2_RELEASE_RADIUS = 3
 CLUSTER_R = np.linspace(0.65, 2.5, 50)  # run_single_shoebox.py:425
 
+# neighbor 0.3 multi; neigh_modify every 1 delay 10 check yes (run_single_shoebox.py:532-533)
+NEIGH_SKIN = 0.3
+NEIGH_DELAY = 10
 # fixes (run_single_shoebox.py:643-647)
 LANGEVIN_T = 1.0
 LANGEVIN_DAMP = 0.5

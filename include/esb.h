@@ -25,7 +25,7 @@ extern "C" {
 #define ESB_MAXT 12          /* atom types are 1..11 (run_single_shoebox.py:23-33); index 0 unused */
 #define ESB_MAX_TABLES 48
 #define ESB_N_SHELL 50       /* cluster_r = linspace(0.65, 2.5, 50) (run_single_shoebox.py:425)    */
-#define ESB_N_COUNTERS 10
+#define ESB_N_COUNTERS 11
 #define ESB_FRAME_DOUBLES 9  /* geneTrack.txt columns (run_single_shoebox.py:1496)                   */
 
 enum {
@@ -95,6 +95,10 @@ int esb_set_coeffs(esb_handle *h, const double bond_k[3], const double bond_r0[3
  * langevin_mode: 1 drag+noise (reference), 2 drag only (zero-noise parity runs), 0 off. */
 int esb_set_fixes(esb_handle *h, double dt, double t_target, double t_damp, int langevin_mode,
                   double wall_eps, double wall_cut);
+/* neighbor SKIN multi; neigh_modify every 1 delay DELAY check yes (run_single_shoebox.py:532-533: 0.3, 10).
+ * A list build happens when DELAY steps have passed since the last one and a bead has moved > SKIN/2;
+ * every run command builds at set-up.  delay 0 = build as soon as a bead has moved > SKIN/2. */
+int esb_set_neighbor(esb_handle *h, double skin, int delay);
 /* pair_style soft + pair_coeff block (run_single_shoebox.py:589-625): symmetric MAXT x MAXT cutoffs */
 int esb_set_soft(esb_handle *h, const double *cut);
 /* pair_style table lookup N + the distinct `pair_coeff I J file KEY cut` tables
@@ -158,7 +162,9 @@ int esb_get_frames_async(esb_handle *h, int chunk_begin, int n_chunks, double *o
 int esb_get_status(esb_handle *h, int *status);                   /* [R] ESB_ST_* bits               */
 /* [R][ESB_N_COUNTERS]: force evaluations, neighbour builds, in-cutoff (ordered) pairs, listed (ordered)
  * pairs summed over evaluations, steps, total_active_steps, then SM cycles spent in the per-atom
- * phase, list builds, force phase, set-up/observation */
+ * phase, list builds, force phase, set-up/observation, and the number of "dangerous builds" (a list
+ * build that was already due at the first step `neigh_modify delay` permits: what LAMMPS prints at the end
+ * of a run) */
 int esb_get_counters(esb_handle *h, int64_t *out);
 int esb_reset_counters(esb_handle *h);
 /* current bond r0 (after fix adapt) and MD step per handle */

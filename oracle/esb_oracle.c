@@ -193,6 +193,7 @@ typedef struct esbo_system {
     esbo_adapt adapt[4];
     /* neighbour list (half, newton on) */
     double skin;
+    int delay, ago;              /* neigh_modify delay N; steps since the last build */
     int *nl_start, *nl, nl_cap;
     int nl_valid;
     /* rng */
@@ -222,6 +223,7 @@ esbo_system *esbo_create(int n, int ntypes)
     s->wall_eps = 100.0; s->wall_cut = 3.0;
     s->langevin_on = 1;
     s->skin = 0.3;
+    s->delay = 10;
     return s;
 }
 
@@ -344,6 +346,8 @@ void esbo_set_seed(esbo_system *s, uint64_t seed, uint64_t eval_counter)
     s->eval_counter = eval_counter;
 }
 void esbo_set_skin(esbo_system *s, double skin) { s->skin = skin; s->nl_valid = 0; }
+/* `neigh_modify every 1 delay N check yes` (run_single_shoebox.py:533, N = 10) */
+void esbo_set_neigh_delay(esbo_system *s, int delay) { s->delay = delay < 0 ? 0 : delay; s->nl_valid = 0; }
 
 /* pair_style soft rc_global; pair_coeff I J A rc (run_single_shoebox.py:589-625).
  * cut is an ESBO_MAXT x ESBO_MAXT symmetric matrix indexed by (type_i, type_j), types 1-based. */
@@ -482,15 +486,27 @@ static void build_neighbors(esbo_system *s)
     free(head); free(next); free(bin3);
 }
 
-static int needs_rebuild(const esbo_system *s)
+/* [LAMMPS-ext] Neighbor::decide + check_distance with `every 1 delay N check yes`: called once per step
+ * (ago++), a build happens when at least N steps have passed since the last one AND some atom has moved
+ * further than skin/2 from where it was at that build.  A build that was already due at the first permitted
+ * step is what LAMMPS reports as a "dangerous build": in the steps before it a pair may have come inside the
+ * cutoff without being in the list -- the reference's settings accept that, and so does this restatement.
+ * Every `run` rebuilds at set-up (nl_valid = 0). */
+static int needs_rebuild(esbo_system *s)
 {
-    if (!s->nl_valid) return 1;
+    if (!s->nl_valid) { s->ago = 0; return 1; }
+    s->ago++;
+    if (s->ago < s->delay) return 0;
     const double trig = 0.25 * s->skin * s->skin;
     for (int i = 0; i < s->n; i++) {
         const double dx = s->x[3 * i] - s->x_build[3 * i];
         const double dy = s->x[3 * i + 1] - s->x_build[3 * i + 1];
         const double dz = s->x[3 * i + 2] - s->x_build[3 * i + 2];
-        if (dx * dx + dy * dy + dz * dz > trig) return 1;
+        if (dx * dx + dy * dy + dz * dz > trig) {
+            if (s->ago == (s->delay > 1 ? s->delay : 1)) s->n_dangerous++;
+            s->ago = 0;
+            return 1;
+        }
     }
     return 0;
 }
@@ -627,6 +643,7 @@ static void compute_forces(esbo_system *s, int with_post, int with_noise)
  * (consumes one noise evaluation index when noise is on). */
 int esbo_compute_forces(esbo_system *s, int with_post, int with_noise, double *f_out, double *e_out)
 {
+    s->nl_valid = 0;   /* the hook is exact at the current positions: complete list */
     compute_forces(s, with_post, with_noise);
     if (f_out) memcpy(f_out, s->f, sizeof(double) * (size_t)s->n * 3);
     if (e_out) memcpy(e_out, s->energy, sizeof(s->energy));

@@ -66,6 +66,7 @@ def lib():
         L.esbo_set_fixes.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
         L.esbo_set_seed.argtypes = [vp, C.c_uint64, C.c_uint64]
         L.esbo_set_skin.argtypes = [vp, C.c_double]
+        L.esbo_set_neigh_delay.argtypes = [vp, C.c_int]
         L.esbo_pair_soft.argtypes = [vp, C.c_double, dp]
         L.esbo_pair_table.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, dp, ip]
         L.esbo_pair_table_remap.argtypes = [vp, ip]
@@ -126,7 +127,7 @@ def build_lookup_table(section, cut: float, tablength: int = 30000):
 class Oracle:
     """One replica on the CPU, driven chunk by chunk with the reference's command stream."""
 
-    def __init__(self, data, tables=None, lookup=None, seed: int = 1, skin: float = 0.3):
+    def __init__(self, data, tables=None, lookup=None, seed: int = 1, skin: float = 0.3, neigh_delay: int = 10):
         """`data`: ShoeboxData.  `tables`: protocol.PairTables.  `lookup`: list of (e, f, innersq, delta)
         per table spec (see `build_lookup_table`)."""
         from enhancershoebox_b200 import protocol as P
@@ -152,6 +153,7 @@ class Oracle:
         self.L.esbo_set_fixes(self.h, P.DT, P.LANGEVIN_T, P.LANGEVIN_DAMP, 1, P.WALL_EPS, P.WALL_CUT)
         self.L.esbo_set_seed(self.h, seed, 0)
         self.L.esbo_set_skin(self.h, skin)
+        self.L.esbo_set_neigh_delay(self.h, neigh_delay)          # neigh_modify every 1 delay 10 check yes (:533)
         self.tables = tables
         self.lookup = lookup
         self._pair = None
@@ -242,7 +244,7 @@ class Oracle:
     def counters(self):
         out = (C.c_longlong * 5)()
         self.L.esbo_get_counters(self.h, out)
-        return dict(evals=out[0], builds=out[1], pairs_in_cut=out[2], pairs_listed=out[3])
+        return dict(evals=out[0], builds=out[1], pairs_in_cut=out[2], pairs_listed=out[3], dangerous=out[4])
 
     def reset_counters(self):
         self.L.esbo_reset_counters(self.h)

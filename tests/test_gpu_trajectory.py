@@ -54,6 +54,11 @@ def test_short_trajectory_matches_oracle(oracle_lib, box11, pair_tables, oracle_
     assert np.abs(xo - x).max() > 0.02                                          # the beads did move
     c = eng.counters()
     assert c["steps"][0] == n_steps and c["evals"][0] == n_steps + 1           # set-up evaluation + one per step
+    # neigh_modify every 1 delay 10 check yes: same build schedule as the oracle (a rounding-level difference in a
+    # displacement can shift one build by a step), never sooner than 10 steps apart
+    oc = orc.counters()
+    assert abs(int(c["builds"][0]) - oc["builds"]) <= 1 and c["builds"][0] <= 1 + n_steps // 10
+    assert abs(int(c["dangerous"][0]) - oc["dangerous"]) <= 1
     eng.close()
 
 

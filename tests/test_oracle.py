@@ -131,3 +131,24 @@ def test_noise_is_reproducible_and_keyed(oracle_lib, box11, pair_tables, oracle_
     assert np.array_equal(f1, f2) and not np.array_equal(f1, f3)
     noise = (f1 - f0)[~np.isin(np.arange(box11.n_atoms), box11.anchors())] / np.sqrt(9600)
     assert np.all(np.abs(noise) <= 0.5 + 1e-9) and abs(noise.mean()) < 0.02 and abs(noise.var() - 1 / 12) < 0.01
+
+
+def test_neighbour_delay_semantics(oracle_lib, box11, pair_tables, oracle_lookup, snapshots):
+    """neigh_modify every 1 delay 10 check yes (run_single_shoebox.py:533): every run builds at set-up, afterwards
+    never sooner than 10 steps after the last build; with delay 0 the list follows the skin/2 rule alone.  The
+    extra builds of delay 0 show that most delay-10 builds were already due ("dangerous builds")."""
+    x, v, t = snapshots["x500"].astype(np.float64), snapshots["v500"].astype(np.float64), snapshots["t500"].astype(np.int32)
+    plan = P.chunk_schedule("genes_stages", n_chunks=501)[500]
+    counts = {}
+    for delay in (10, 0):
+        o = oracle_lib.Oracle(box11, pair_tables, oracle_lookup, seed=4, neigh_delay=delay)
+        o.set_state(t, x, v)
+        o.apply_plan(plan)
+        o.reset_counters()
+        assert o.run(200) == 0
+        counts[delay] = o.counters()
+    c10, c0 = counts[10], counts[0]
+    assert c10["evals"] == c0["evals"] == 201
+    assert 2 <= c10["builds"] <= 1 + 200 // 10                     # set-up + at most one per 10 steps
+    assert c0["builds"] > c10["builds"] and c0["dangerous"] == 0
+    assert 0 < c10["dangerous"] <= c10["builds"] - 1
