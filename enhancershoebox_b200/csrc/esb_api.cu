@@ -112,6 +112,15 @@ struct esb_handle {
     unsigned short *d_hist = nullptr;
     unsigned long long *d_counters = nullptr;
     int *d_sched = nullptr;
+    // topology as given (kept for esb_set_actin) and the dynamic actin state
+    std::vector<int> bonds, angles;
+    esb_actin_params act = {};
+    bool have_actin = false;
+    unsigned int *d_act_link = nullptr;
+    unsigned short *d_act_lists = nullptr;
+    int *d_act_stats = nullptr;
+    unsigned short *d_act_hist = nullptr;
+    size_t bterm_stride = 0, spec_stride = 0;
     int n_sm = 148;
     Layout lay = {0, 0, 0, 0};
     std::vector<ReplicaScalars> rs_host;
@@ -283,6 +292,8 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     k.qcx = h->qcx; k.qcy = h->qcy; k.qcz = h->qcz; k.qcell_inv = (float)(1.0 / h->quad_edge);
     k.pos4 = h->d_pos4; k.vel4 = h->d_vel4; k.rs = h->d_rs; k.frozen = h->d_frozen;
     k.bterm = h->d_bterm; k.spec = h->d_spec; k.n_topo_pad = h->n_topo_pad;
+    k.bterm_stride = h->bterm_stride; k.spec_stride = h->spec_stride;
+    if (h->have_actin) { k.act = h->act; k.act_link = h->d_act_link; k.act_lists = h->d_act_lists; k.act_stats = h->d_act_stats; k.act_hist = h->d_act_hist; }
     k.setups = h->d_setups;
     k.tabs = array_flavour ? h->d_tabs_array : h->d_tabs_closed;
     k.n_tables = (int)h->tables.size();
@@ -370,6 +381,7 @@ int esb_destroy(esb_handle *h)
     cudaFree(h->d_tabval); cudaFree(h->d_tabe); cudaFree(h->d_nl_pool); cudaFree(h->d_nl_qinfo); cudaFree(h->d_descs);
     cudaFree(h->d_enh); cudaFree(h->d_s5p); cudaFree(h->d_cluster_r); cudaFree(h->d_frames); cudaFree(h->d_rawd); cudaFree(h->d_hist);
     cudaFree(h->d_counters); cudaFree(h->d_sched);
+    cudaFree(h->d_act_link); cudaFree(h->d_act_lists); cudaFree(h->d_act_stats); cudaFree(h->d_act_hist);
     delete h;
     return ESB_OK;
 }
@@ -390,7 +402,10 @@ int esb_set_topology(esb_handle *h, int n_bonds, const int *bonds, int n_angles,
     if (!h || n_bonds < 0 || n_angles < 0 || n_frozen < 0) return fail(ESB_EINVAL, "bad argument");
     CK(cudaSetDevice(h->device));
     const int N = h->N;
-    int n_topo = 0;
+    if (bonds != h->bonds.data()) h->bonds.assign(bonds, bonds + (size_t)3 * n_bonds);
+    if (angles != h->angles.data()) h->angles.assign(angles, angles + (size_t)4 * n_angles);
+    bonds = h->bonds.data(); angles = h->angles.data();
+    int n_topo = h->have_actin ? h->act.first + h->act.count : 0;    // dynamic actin: every actin bead owns table rows
     for (int b = 0; b < n_bonds; b++)
         for (int q = 1; q <= 2; q++) {
             const int a = bonds[3 * b + q];
@@ -446,13 +461,29 @@ int esb_set_topology(esb_handle *h, int n_bonds, const int *bonds, int n_angles,
             cur.swap(nxt);
         }
     }
-    h->frozen.assign(h->n_pad, 0);
-    for (int q = 0; q < n_frozen; q++) {
-        if (frozen[q] < 0 || frozen[q] >= N) return fail(ESB_EINVAL, "frozen atom %d out of range", frozen[q]);
-        h->frozen[frozen[q]] = 1;
+    if (frozen) {
+        h->frozen.assign(h->n_pad, 0);
+        for (int q = 0; q < n_frozen; q++) {
+            if (frozen[q] < 0 || frozen[q] >= N) return fail(ESB_EINVAL, "frozen atom %d out of range", frozen[q]);
+            h->frozen[frozen[q]] = 1;
+        }
     }
     int rc;
-    if ((rc = dev_upload(&h->d_bterm, bt)) || (rc = dev_upload(&h->d_spec, sp)) || (rc = dev_upload(&h->d_frozen, h->frozen))) return rc;
+    if (h->have_actin) {
+        // bonds, angles and exclusions are per-replica state: R copies of the tables
+        std::vector<uint2> btr((size_t)h->R * bt.size());
+        std::vector<unsigned short> spr((size_t)h->R * sp.size());
+        for (int r = 0; r < h->R; r++) {
+            std::copy(bt.begin(), bt.end(), btr.begin() + (size_t)r * bt.size());
+            std::copy(sp.begin(), sp.end(), spr.begin() + (size_t)r * sp.size());
+        }
+        h->bterm_stride = bt.size(); h->spec_stride = sp.size();
+        if ((rc = dev_upload(&h->d_bterm, btr)) || (rc = dev_upload(&h->d_spec, spr))) return rc;
+    } else {
+        h->bterm_stride = h->spec_stride = 0;
+        if ((rc = dev_upload(&h->d_bterm, bt)) || (rc = dev_upload(&h->d_spec, sp))) return rc;
+    }
+    if ((rc = dev_upload(&h->d_frozen, h->frozen))) return rc;
     h->n_topo = n_topo; h->n_topo_pad = ntp; h->have_topo = true;
     if (h->have_state) {
         const size_t tot = (size_t)h->R * h->n_pad;
@@ -479,6 +510,101 @@ int esb_set_fixes(esb_handle *h, double dt, double t_target, double t_damp, int 
         return fail(ESB_EINVAL, "bad fix parameters");
     h->dt = dt; h->t_target = t_target; h->t_damp = t_damp; h->langevin_mode = langevin_mode;
     h->wall_eps = wall_eps; h->wall_cut = wall_cut;
+    return ESB_OK;
+}
+
+int esb_set_actin(esb_handle *h, const esb_actin_params *p)
+{
+    if (!h || !p) return fail(ESB_EINVAL, "NULL argument");
+    if (!h->have_topo) return fail(ESB_ESTATE, "esb_set_topology must be called first");
+    if (p->first < 0 || p->count < 2 || p->first + p->count > h->N || p->count > 16000 || p->max_tries < 1)
+        return fail(ESB_EINVAL, "bad actin range [%d, %d) of %d atoms", p->first, p->first + p->count, h->N);
+    if ((size_t)p->count * 29 > (size_t)12 * h->n_pad) return fail(ESB_EINVAL, "too many actin beads for the event scratch");
+    CK(cudaSetDevice(h->device));
+    h->act = *p; h->have_actin = true;
+    // per-replica tables (rows for every actin bead) from the stored topology
+    int rc = esb_set_topology(h, (int)(h->bonds.size() / 3), h->bonds.data(), (int)(h->angles.size() / 4), h->angles.data(), 0, nullptr);
+    if (rc) return rc;
+    // initial filaments: the type-2 bonds among the actin beads; the lower atom id is towards the plus end
+    const int first = p->first, count = p->count;
+    std::vector<unsigned int> link(count, 0xffffffffu);
+    for (size_t b = 0; b < h->bonds.size() / 3; b++) {
+        int i = h->bonds[3 * b + 1], j = h->bonds[3 * b + 2];
+        const bool ai = i >= first && i < first + count, aj = j >= first && j < first + count;
+        if (!ai && !aj) continue;
+        if (!(ai && aj) || h->bonds[3 * b] != 2) return fail(ESB_EINVAL, "bond %zu ties an actin bead to something that is not an actin filament", b);
+        if (i > j) std::swap(i, j);
+        if ((link[i - first] >> 16) != ESB_NOLINK || (link[j - first] & 0xffffu) != ESB_NOLINK)
+            return fail(ESB_EINVAL, "actin bonds do not form linear filaments ordered by atom id");
+        link[i - first] = (link[i - first] & 0x0000ffffu) | ((unsigned int)j << 16);
+        link[j - first] = (link[j - first] & 0xffff0000u) | (unsigned int)i;
+    }
+    std::vector<unsigned short> lists(ESB_ACT_WORDS(count), 0);
+    unsigned short *fr = lists.data() + 2, *fplus = fr + count, *fminus = fplus + count;
+    int nfree = 0, nfil = 0;
+    for (int k = 0; k < count; k++) {
+        if (link[k] == 0xffffffffu) { fr[nfree++] = (unsigned short)(first + k); continue; }
+        if ((link[k] & 0xffffu) != ESB_NOLINK) continue;               // not a plus end
+        int b = first + k;
+        fplus[nfil] = (unsigned short)b;
+        while ((link[b - first] >> 16) != ESB_NOLINK) b = (int)(link[b - first] >> 16);
+        fminus[nfil++] = (unsigned short)b;
+    }
+    lists[0] = (unsigned short)nfree; lists[1] = (unsigned short)nfil;
+    std::vector<unsigned int> linkr((size_t)h->R * count);
+    std::vector<unsigned short> listr((size_t)h->R * lists.size());
+    for (int r = 0; r < h->R; r++) {
+        std::copy(link.begin(), link.end(), linkr.begin() + (size_t)r * count);
+        std::copy(lists.begin(), lists.end(), listr.begin() + (size_t)r * lists.size());
+    }
+    if ((rc = dev_upload(&h->d_act_link, linkr)) || (rc = dev_upload(&h->d_act_lists, listr))) return rc;
+    if (h->n_chunks > 0) {
+        if ((rc = dev_alloc(&h->d_act_stats, (size_t)h->R * h->n_chunks * 6)) || (rc = dev_alloc(&h->d_act_hist, (size_t)h->R * h->n_chunks * (ESB_N_SHELL - 1)))) return rc;
+        CK(cudaMemset(h->d_act_stats, 0, (size_t)h->R * h->n_chunks * 6 * sizeof(int)));
+        CK(cudaMemset(h->d_act_hist, 0, (size_t)h->R * h->n_chunks * (ESB_N_SHELL - 1) * sizeof(unsigned short)));
+    }
+    return ESB_OK;
+}
+
+int esb_get_actin(esb_handle *h, int *plus, int *minus, int *n_free, int *free_list, int *n_fil, int *fil_plus)
+{
+    if (!h || !h->have_actin) return fail(ESB_ESTATE, "esb_set_actin has not been called");
+    CK(cudaSetDevice(h->device));
+    const int count = h->act.count;
+    std::vector<unsigned int> link((size_t)h->R * count);
+    std::vector<unsigned short> lists((size_t)h->R * ESB_ACT_WORDS(count));
+    CK(cudaMemcpy(link.data(), h->d_act_link, link.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lists.data(), h->d_act_lists, lists.size() * sizeof(unsigned short), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < h->R; r++) {
+        const unsigned short *L = lists.data() + (size_t)r * ESB_ACT_WORDS(count);
+        for (int k = 0; k < count; k++) {
+            const unsigned int w = link[(size_t)r * count + k];
+            if (plus) plus[(size_t)r * count + k] = (w & 0xffffu) == ESB_NOLINK ? -1 : (int)(w & 0xffffu);
+            if (minus) minus[(size_t)r * count + k] = (w >> 16) == ESB_NOLINK ? -1 : (int)(w >> 16);
+            if (free_list) free_list[(size_t)r * count + k] = k < L[0] ? (int)L[2 + k] : -1;
+            if (fil_plus) fil_plus[(size_t)r * count + k] = k < L[1] ? (int)L[2 + count + k] : -1;
+        }
+        if (n_free) n_free[r] = L[0];
+        if (n_fil) n_fil[r] = L[1];
+    }
+    return ESB_OK;
+}
+
+int esb_get_actin_frames(esb_handle *h, int chunk_begin, int n_chunks, int *stats, int *hist)
+{
+    if (!h || !stats) return fail(ESB_EINVAL, "NULL argument");
+    if (!h->have_actin || !h->d_act_stats) return fail(ESB_ESTATE, "no actin records (esb_set_actin + esb_set_schedule first)");
+    if (chunk_begin < 0 || n_chunks < 1 || chunk_begin + n_chunks > h->n_chunks) return fail(ESB_EINVAL, "chunk range outside the schedule");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy2D(stats, (size_t)n_chunks * 6 * sizeof(int), h->d_act_stats + (size_t)chunk_begin * 6, (size_t)h->n_chunks * 6 * sizeof(int),
+                    (size_t)n_chunks * 6 * sizeof(int), h->R, cudaMemcpyDeviceToHost));
+    if (hist) {
+        const int nb = ESB_N_SHELL - 1;
+        std::vector<unsigned short> tmp((size_t)h->R * n_chunks * nb);
+        CK(cudaMemcpy2D(tmp.data(), (size_t)n_chunks * nb * 2, h->d_act_hist + (size_t)chunk_begin * nb, (size_t)h->n_chunks * nb * 2,
+                        (size_t)n_chunks * nb * 2, h->R, cudaMemcpyDeviceToHost));
+        for (size_t q = 0; q < tmp.size(); q++) hist[q] = tmp[q];
+    }
     return ESB_OK;
 }
 
@@ -718,6 +844,11 @@ int esb_set_schedule(esb_handle *h, int n_chunks, const esb_chunk_desc *descs)
         CK(cudaMemset(h->d_rawd, 0, (size_t)h->R * n_chunks * 2 * sizeof(double)));
         CK(cudaMemset(h->d_frames, 0, (size_t)h->R * n_chunks * ESB_FRAME_DOUBLES * sizeof(double)));
         CK(cudaMemset(h->d_hist, 0, (size_t)h->R * n_chunks * (ESB_N_SHELL - 1) * sizeof(unsigned short)));
+    }
+    if (h->have_actin && (n_chunks != h->n_chunks || !h->d_act_stats)) {
+        if ((rc = dev_alloc(&h->d_act_stats, (size_t)h->R * n_chunks * 6)) || (rc = dev_alloc(&h->d_act_hist, (size_t)h->R * n_chunks * (ESB_N_SHELL - 1)))) return rc;
+        CK(cudaMemset(h->d_act_stats, 0, (size_t)h->R * n_chunks * 6 * sizeof(int)));
+        CK(cudaMemset(h->d_act_hist, 0, (size_t)h->R * n_chunks * (ESB_N_SHELL - 1) * sizeof(unsigned short)));
     }
     h->n_chunks = n_chunks;
     // keep a host copy for validation at run time

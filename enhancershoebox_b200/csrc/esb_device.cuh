@@ -26,6 +26,8 @@
 #define ESB_NL_STRIDE 1024           // list arena per bead (entries); LAMMPS: neigh_modify one 10000
 #define ESB_NCLASS 6                 // species classes for the row sort: chromatin-like, actin, RBP, RNP, Ser5P, gene body (induced/active)
 #define ESB_N_COUNTERS 11             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases, dangerous builds
+#define ESB_ACT_WORDS(count) (2 + 3 * (count))
+#define ESB_NOLINK 0xffffu
 #define ESB_N_SETUPS 9               // 0 = pair soft, 1..4 = table maps 0..3 (closed form + patch), 5..8 = same maps, array lookups
 
 // One (KEY,cut) table, 48 bytes, read in the force loop as two float4 (+ two doubles on the rare
@@ -92,9 +94,16 @@ struct KArgs {
     float4 *vel4;             // [R][n_pad]
     ReplicaScalars *rs;       // [R]
     const unsigned char *frozen;     // [n_pad]
-    const uint2 *bterm;       // [ESB_MAX_TERMS][n_topo_pad]
-    const unsigned short *spec;      // [n_topo_pad][ESB_MAX_SPEC]
+    uint2 *bterm;             // [ESB_MAX_TERMS][n_topo_pad]  (+ r * bterm_stride: per replica with actin dynamics)
+    unsigned short *spec;     // [n_topo_pad][ESB_MAX_SPEC]   (+ r * spec_stride)
     int n_topo_pad;
+    size_t bterm_stride, spec_stride;
+    // actin polymerisation dynamics (act.count == 0: off)
+    esb_actin_params act;
+    unsigned int *act_link;   // [R][act.count]  neighbour towards the plus end | neighbour towards the minus end << 16 (atom ids, 0xffff none)
+    unsigned short *act_lists;       // [R][ESB_ACT_WORDS(count)]: n_free, n_fil, free[count], fil_plus[count], fil_minus[count]
+    int *act_stats;           // [R][max_chunks][6]
+    unsigned short *act_hist; // [R][max_chunks][49]
     const PairSetup *setups;  // [ESB_N_SETUPS]
     const DevTab *tabs;       // [n_tables] (the launch picks the closed-form or the array flavour)
     int n_tables;

@@ -378,7 +378,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
                         bool ok = live && (r2 < cs) && (j != ia[b]);
                         if (TOPO) {
                             if (ok && j < n_topo && ia[b] < n_topo) {
-                                const uint4 sp4 = *reinterpret_cast<const uint4 *>(a.spec + (size_t)ia[b] * ESB_MAX_SPEC);
+                                const uint4 sp4 = __ldcg(reinterpret_cast<const uint4 *>(a.spec + (size_t)r * a.spec_stride + (size_t)ia[b] * ESB_MAX_SPEC));
                                 const unsigned int jj = (unsigned int)j;
                                 ok = !((sp4.x & 0xffffu) == jj || (sp4.x >> 16) == jj || (sp4.y & 0xffffu) == jj || (sp4.y >> 16) == jj ||
                                        (sp4.z & 0xffffu) == jj || (sp4.z >> 16) == jj || (sp4.w & 0xffffu) == jj || (sp4.w >> 16) == jj);
@@ -454,19 +454,20 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
 // [LAMMPS-ext] AngleCosine::compute   E = K (1 + cos theta)  (angle_coeff, run_single_shoebox.py:583-584)
 // ------------------------------------------------------------------------------------------------
 template <bool ENERGY>
-__device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, const float r0_1, const float r0_2,
+__device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, const int r, const float r0_1, const float r0_2,
                                               double &e_bond, double &e_angle)
 {
     const int n = a.n_atoms, n_topo = a.n_topo, ntp = a.n_topo_pad;
+    const uint2 *bterm = a.bterm + (size_t)r * a.bterm_stride;     // per replica when the actin topology is dynamic
     for (int i = threadIdx.x; i < n; i += ESB_THREADS) {
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
         if (i < n_topo) {
             const float4 pi = S.pos[i];
 #pragma unroll 1
             for (int t = 0; t < ESB_MAX_TERMS; t++) {
-                const uint2 term = a.bterm[(size_t)t * ntp + i];
+                const uint2 term = __ldcg(&bterm[(size_t)t * ntp + i]);      // (another SM may have rewritten it one chunk ago)
                 const int kind = term.y & 0xff, type = (term.y >> 8) & 0xff;
-                if (kind == 0) continue;
+                if (kind == 0) break;                                         // a bead's terms are stored without gaps
                 const float4 pa = S.pos[term.x & 0xffffu];
                 if (kind == 1) {
                     const float dx = pi.x - pa.x, dy = pi.y - pa.y, dz = pi.z - pa.z;
@@ -532,7 +533,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
     const int lane = tid & 31;
     const int gl = lane & (ESB_G - 1), grp = lane / ESB_G;
     double e_pair = 0.0, e_bond = 0.0, e_angle = 0.0;
-    bonded_forces<ENERGY>(S, a, r0_1, r0_2, e_bond, e_angle);
+    bonded_forces<ENERGY>(S, a, r, r0_1, r0_2, e_bond, e_angle);
     if (tid == 0) S.misc[M_QCTR] = 0;
     __syncthreads();
     const unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESB_NL_STRIDE;
@@ -879,6 +880,246 @@ __device__ __noinline__ void observe(const KArgs &a, int r, const esb_chunk_desc
 }
 
 
+
+// ------------------------------------------------------------------------------------------------
+// Actin events between two `run` commands (run_single_shoebox.py:969-1298): nucleation of two free
+// monomers, polymerisation at the plus end (every chunk) and at the minus end (every 40th),
+// depolymerisation at the minus end (every 5th), each with the relocation of the moved monomer by
+// rejection sampling (`set atom ID x y z`), followed by what `create_bonds single/bond 2`,
+// `single/angle 2` and `delete_bonds ... remove special` do to the topology.  Filaments are linear, so the
+// whole topology of the actin beads is two links per bead (neighbour towards the plus / minus end) from
+// which bonds, angles and 1-2/1-3/1-4 exclusions are re-derived after the events.  The bookkeeping
+// lists keep the reference's order (free_actin, filament_details).  Python's unseeded random /
+// numpy.random are replaced by Philox draws keyed by (replica seed; chunk, draw index) -- the test-side
+// restatement of these lines consumes the same stream in the same order; all decisions are taken in fp64 with
+// numpy's evaluation order on the fp32 coordinates, so device and oracle agree event by event.
+// ------------------------------------------------------------------------------------------------
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 d3_of(const float4 q) { D3 o; o.x = (double)q.x; o.y = (double)q.y; o.z = (double)q.z; return o; }
+__device__ __forceinline__ double d3_dist(const D3 a, const D3 b)
+{
+    const double dx = __dsub_rn(a.x, b.x), dy = __dsub_rn(a.y, b.y), dz = __dsub_rn(a.z, b.z);
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
+template <int NP>
+__device__ __noinline__ void actin_events(const KArgs &a, const int r, const esb_chunk_desc &d, const ReplicaScalars &rs, const int slot)
+{
+    const Smem S = carve<NP>(a);
+    const int tid = threadIdx.x;
+    const int first = a.act.first, count = a.act.count;
+    // volatile: this replica's bookkeeping was last written by another SM (L1 is not coherent)
+    volatile unsigned int *link = a.act_link + (size_t)r * count;            // indexed by atom - first
+    volatile unsigned short *L = a.act_lists + (size_t)r * ESB_ACT_WORDS(count);
+    volatile unsigned short *fr = L + 2, *fplus = fr + count, *fminus = fplus + count;
+    // scratch in the (idle) force arrays: stale free positions, a snapshot of the free list, flags
+    double *fpos = reinterpret_cast<double *>(S.fx);                         // [3 * count]
+    unsigned short *snap = reinterpret_cast<unsigned short *>(fpos + 3 * count);      // [count]
+    unsigned char *flag = reinterpret_cast<unsigned char *>(snap + count);            // [count]
+    auto lp = [&](int atom) { return (int)(link[atom - first] & 0xffffu); };          // towards the plus end
+    auto lm = [&](int atom) { return (int)(link[atom - first] >> 16); };              // towards the minus end
+    auto set_lp = [&](int atom, int v) { link[atom - first] = (link[atom - first] & 0xffff0000u) | (unsigned int)v; };
+    auto set_lm = [&](int atom, int v) { link[atom - first] = (link[atom - first] & 0x0000ffffu) | ((unsigned int)v << 16); };
+    if ((d.actin_flags & 1) && tid == 0) {
+        const int i = d.chunk_index;
+        uint32_t m = 0;
+        auto draw = [&](uint32_t o[4]) { philox4x32_10((uint32_t)i, m++, 0u, 3u, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), o); };
+        auto uni = [](uint32_t w) { return (double)(w >> 8) * 0x1p-24; };
+        auto place = [&](int atom, const D3 q) {
+            float4 p = S.pos[atom];
+            p.x = (float)q.x; p.y = (float)q.y; p.z = (float)q.z;
+            S.pos[atom] = p;
+        };
+        // new_loc = np.random.uniform(low=c-h, high=c+h, size=(1,3))
+        auto sample = [&](const D3 c, const double h) {
+            uint32_t o[4];
+            draw(o);
+            D3 q;
+            const double lx = __dsub_rn(c.x, h), ly = __dsub_rn(c.y, h), lz = __dsub_rn(c.z, h);
+            q.x = __dadd_rn(lx, __dmul_rn(__dsub_rn(__dadd_rn(c.x, h), lx), uni(o[0])));
+            q.y = __dadd_rn(ly, __dmul_rn(__dsub_rn(__dadd_rn(c.y, h), ly), uni(o[1])));
+            q.z = __dadd_rn(lz, __dmul_rn(__dsub_rn(__dadd_rn(c.z, h), lz), uni(o[2])));
+            return q;
+        };
+        auto free_remove = [&](int &nfree, int atom) {
+            int w = 0;
+            for (int k = 0; k < nfree; k++) if (fr[k] != atom) fr[w++] = fr[k];
+            nfree = w;
+        };
+        int nfree = L[0], nfil = L[1];
+        const double sh_lo = a.act.shell_lo, sh_hi = a.act.shell_hi, half = a.act.shell_hi;
+        // ---------------- nucleation (:973-1027) ----------------
+        {
+            for (int k = 0; k < nfree; k++) { const D3 q = d3_of(S.pos[fr[k]]); fpos[3 * k] = q.x; fpos[3 * k + 1] = q.y; fpos[3 * k + 2] = q.z; flag[k] = 0; }
+            unsigned short *pc = snap;                                        // pairs: plus-end atom, minus-end atom
+            int npairs = 0;
+            auto in_pairs = [&](int atom) { for (int q = 0; q < 2 * npairs; q++) if (pc[q] == atom) return true; return false; };
+            for (int j = 0; j < nfree; j++) {
+                uint32_t o[4];
+                draw(o);
+                if (!(uni(o[0]) <= a.act.p_nucleation)) continue;
+                const int curr = fr[j];
+                if (in_pairs(curr) || nfree < 2) continue;                   // (the reference finds this out later; no draw in between)
+                const D3 c = d3_of(S.pos[curr]);
+                double dmin = 1e300;
+                int kmin = -1;
+                for (int k = 0; k < nfree; k++) {
+                    if (k == j) continue;
+                    D3 q; q.x = fpos[3 * k]; q.y = fpos[3 * k + 1]; q.z = fpos[3 * k + 2];
+                    const double dd = d3_dist(c, q);
+                    if (dd < dmin) { dmin = dd; kmin = k; }
+                }
+                if (!(dmin < a.act.monomer_radius)) continue;
+                const int tba = fr[kmin];
+                if (in_pairs(tba)) continue;
+                pc[2 * npairs] = (unsigned short)curr; pc[2 * npairs + 1] = (unsigned short)tba; npairs++;
+                int n_tries = 1;
+                D3 q;
+                for (;;) {
+                    n_tries++;
+                    q = sample(c, half);
+                    const double dd = d3_dist(c, q);
+                    if (dd > sh_lo && dd < sh_hi) break;
+                    if (n_tries > a.act.max_tries) break;
+                }
+                if (n_tries > a.act.max_tries) continue;
+                place(tba, q);
+            }
+            for (int q = 0; q < npairs; q++) {                               // create_bonds single/bond 2 curr to_be_added (:1029-1038)
+                const int curr = pc[2 * q], tba = pc[2 * q + 1];
+                set_lm(curr, tba); set_lp(tba, curr);
+                free_remove(nfree, curr); free_remove(nfree, tba);
+                fplus[nfil] = (unsigned short)curr; fminus[nfil] = (unsigned short)tba; nfil++;
+            }
+        }
+        // ---------------- polymerisation (:1062-1135) ----------------
+        auto grow = [&](const int j, const bool plus_end) {
+            int curr = plus_end ? fplus[j] : fminus[j];
+            int adj = plus_end ? lm(curr) : lp(curr);
+            const D3 c0 = d3_of(S.pos[curr]);
+            const int n0 = nfree;
+            for (int k = 0; k < n0; k++) { snap[k] = fr[k]; flag[k] = d3_dist(c0, d3_of(S.pos[fr[k]])) < a.act.end_radius; }
+            for (int k = 0; k < n0; k++) {
+                if (!flag[k]) continue;
+                const int tba = snap[k];
+                const D3 c = d3_of(S.pos[curr]), ca = d3_of(S.pos[adj]);
+                int n_tries = 0;
+                D3 q;
+                for (;;) {
+                    n_tries++;
+                    q = sample(c, half);
+                    const double dd = d3_dist(c, q), da = d3_dist(ca, q);
+                    if (dd > sh_lo && dd < sh_hi && da > a.act.adj_min) break;
+                    if (n_tries > a.act.max_tries) break;
+                }
+                if (n_tries > a.act.max_tries) continue;
+                place(tba, q);
+                if (plus_end) { set_lp(curr, tba); set_lm(tba, curr); fplus[j] = (unsigned short)tba; }
+                else { set_lm(curr, tba); set_lp(tba, curr); fminus[j] = (unsigned short)tba; }
+                free_remove(nfree, tba);
+                adj = curr; curr = tba;
+            }
+        };
+        {
+            const int nf0 = nfil;
+            for (int j = 0; j < nf0; j++) {
+                uint32_t o[4];
+                draw(o);
+                if (uni(o[0]) <= a.act.p_on) grow(j, true);
+                if (d.actin_flags & 2) {
+                    draw(o);
+                    if (uni(o[0]) <= a.act.p_on) grow(j, false);
+                }
+            }
+        }
+        // ---------------- depolymerisation at the minus end (:1168-1203) ----------------
+        if (d.actin_flags & 4) {
+            for (int j = 0; j < nfil; j++) {
+                const int curr = fminus[j], nxt = lp(curr);
+                link[curr - first] = 0xffffffffu;
+                set_lm(nxt, ESB_NOLINK);
+                fr[nfree++] = (unsigned short)curr;
+                fminus[j] = (unsigned short)nxt;
+                const D3 c = d3_of(S.pos[curr]), cn = d3_of(S.pos[nxt]);
+                int n_tries = 0;
+                D3 q;
+                for (;;) {
+                    n_tries++;
+                    q = sample(c, a.act.free_box);
+                    if (d3_dist(cn, q) > a.act.free_min) break;
+                    if (n_tries > a.act.max_tries) break;
+                }
+                if (!(n_tries > a.act.max_tries)) place(curr, q);
+                if (lp(nxt) == (int)ESB_NOLINK) {                            // a filament of length 1 is no filament (:1196-1203)
+                    fr[nfree++] = (unsigned short)nxt;
+                    fplus[j] = ESB_NOLINK;
+                }
+            }
+            int w = 0;
+            for (int j = 0; j < nfil; j++) if (fplus[j] != ESB_NOLINK) { fplus[w] = fplus[j]; fminus[w] = fminus[j]; w++; }
+            nfil = w;
+        }
+        L[0] = (unsigned short)nfree; L[1] = (unsigned short)nfil;
+    }
+    __syncthreads();
+    // ---- bonds, angles and exclusions of the actin beads from their links (kind-major, no gaps) ----
+    if (d.actin_flags & 1) {
+        uint2 *bt = a.bterm + (size_t)r * a.bterm_stride;
+        unsigned short *sp = a.spec + (size_t)r * a.spec_stride;
+        const int ntp = a.n_topo_pad;
+        for (int k = tid; k < count; k += ESB_THREADS) {
+            const int b = first + k;
+            const unsigned int NO = ESB_NOLINK;
+            const unsigned int p1 = lp(b), m1 = lm(b);
+            const unsigned int p2 = p1 != NO ? lp(p1) : NO, m2 = m1 != NO ? lm(m1) : NO;
+            const unsigned int p3 = p2 != NO ? lp(p2) : NO, m3 = m2 != NO ? lm(m2) : NO;
+            int nt = 0;
+            auto add = [&](unsigned int x, unsigned int y, int kind) { bt[(size_t)nt * ntp + b] = make_uint2(x | (y << 16), (unsigned int)kind | (2u << 8)); nt++; };
+            if (p1 != NO) add(p1, 0u, 1);
+            if (m1 != NO) add(m1, 0u, 1);
+            if (p2 != NO) add(p1, p2, 2);
+            if (m2 != NO) add(m1, m2, 2);
+            if (p1 != NO && m1 != NO) add(p1, m1, 3);
+            for (; nt < ESB_MAX_TERMS; nt++) bt[(size_t)nt * ntp + b] = make_uint2(0u, 0u);
+            unsigned short *row = sp + (size_t)b * ESB_MAX_SPEC;
+            row[0] = (unsigned short)p1; row[1] = (unsigned short)p2; row[2] = (unsigned short)p3;
+            row[3] = (unsigned short)m1; row[4] = (unsigned short)m2; row[5] = (unsigned short)m3;
+            row[6] = 0xffff; row[7] = 0xffff;
+        }
+    }
+    // ---- actinTrack / actinAroundCluster records of this chunk (:1523-1544) ----
+    if (slot < a.max_chunks) {
+        for (int k = tid; k < ESB_N_SHELL; k += ESB_THREADS) S.misc[M_HIST + k] = 0;
+        __syncthreads();
+        const Layout Lay = a.lay;
+        for (int k = tid; k < count; k += ESB_THREADS) {
+            const float4 q = S.pos[first + k];
+            const double qx = (double)q.x, qy = (double)q.y, qz = (double)q.z;
+            double dmin = 1e300;
+            for (int e = 0; e < Lay.n_enh; e++) dmin = fmin(dmin, dist_sq3(qx, qy, qz, S.pos[a.enh_idx[e]]));
+            const double dm = __dsqrt_rn(dmin);
+            int k0 = ESB_N_SHELL;
+            for (int c = 0; c < ESB_N_SHELL; c++) if (dm < a.cluster_r[c]) { k0 = c; break; }
+            if (k0 >= 1 && k0 < ESB_N_SHELL) atomicAdd(&S.misc[M_HIST + k0 - 1], 1);
+        }
+        __syncthreads();
+        for (int k = tid; k < ESB_N_SHELL - 1; k += ESB_THREADS)
+            a.act_hist[((size_t)r * a.max_chunks + slot) * (ESB_N_SHELL - 1) + k] = (unsigned short)S.misc[M_HIST + k];
+        if (tid == 0) {
+            const int nfree = L[0], nfil = L[1];
+            int sum = 0, sum2 = 0, mn = 1 << 30, mx = 0;
+            for (int j = 0; j < nfil; j++) {
+                int len = 1;
+                for (int b = fplus[j]; lm(b) != (int)ESB_NOLINK; b = lm(b)) len++;
+                sum += len; sum2 += len * len; mn = min(mn, len); mx = max(mx, len);
+            }
+            int *o = a.act_stats + ((size_t)r * a.max_chunks + slot) * 6;
+            o[0] = nfil; o[1] = sum; o[2] = sum2; o[3] = nfree; o[4] = nfil ? mn : 0; o[5] = mx;
+        }
+    }
+    __syncthreads();
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -986,6 +1227,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         }
         const unsigned long long n_pairs = (unsigned int)S.misc[M_PAIRS];
         if (!failed && d.observe) observe<NP>(a, r, d, rs, delt, sig_nm, c);
+        if (!failed && d.observe && a.act.count > 0) actin_events<NP>(a, r, d, rs, c);
         ESB_TICK(t_obs)
         __syncthreads();
         failed |= S.misc[M_FAIL];
@@ -1039,7 +1281,7 @@ esb_forces_kernel(const __grid_constant__ KArgs a, const int pair_mode, const in
     double en[3] = {0.0, 0.0, 0.0};
     if (pair_mode == 1) force_phase<NP, 1, true>(a, r, soft_a, (float)rs.r0[1], (float)rs.r0[2], en);
     else if (pair_mode == 2) force_phase<NP, 2, true>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], en);
-    else { double eb = 0.0, ea = 0.0; bonded_forces<true>(S, a, (float)rs.r0[1], (float)rs.r0[2], eb, ea); en[1] = eb; en[2] = ea; }
+    else { double eb = 0.0, ea = 0.0; bonded_forces<true>(S, a, r, (float)rs.r0[1], (float)rs.r0[2], eb, ea); en[1] = eb; en[2] = ea; }
     __syncthreads();
     double e_wall = 0.0;
     for (int i = tid; i < a.n_atoms; i += ESB_THREADS) {

@@ -82,10 +82,9 @@ def run_condition(driver: str, a: dict, n_chunks: int | None = None, device: int
     repeats that could not be completed."""
     condition = a["condition"]
     is_actin = driver == "shoebox" and a.get("actin", 0) > 0 and condition != "noactin"
-    if is_actin and condition not in ("LatB", "SwinA_nopol"):
-        raise SystemExit(f"condition {condition!r} with -z {a['actin']} needs the actin polymerisation events "
-                         "(run_single_shoebox.py:969-1298), which this engine does not run yet; "
-                         "the static-topology actin conditions are LatB and SwinA_nopol (:459-460)")
+    # actin polymerisation events (run_single_shoebox.py:969-1298) run in every actin condition except the
+    # static-topology ones, LatB and SwinA_nopol (:459-460)
+    p_nucleation = float(a.get("p_nucleation", 0.0)) if is_actin else None
     if data is None:
         path = datafile.input_file_name(a["box"], a["promoter"], is_actin, a.get("actin") or None)
         if not os.path.exists(path):
@@ -105,11 +104,12 @@ def run_condition(driver: str, a: dict, n_chunks: int | None = None, device: int
             with open(os.path.join(a["out"], "parallel_counter", f"progress_run{r}.txt"), "w") as f:
                 f.write(f"{r},0")
         eng = ShoeboxBatch(data, n_replicas=len(pending), driver=driver, condition=condition, device=device, table_file=table_file,
-                           seeds=seeds, thresholds=a["threshold"], activations=a["activation"])
+                           seeds=seeds, thresholds=a["threshold"], activations=a["activation"], p_nucleation=p_nucleation)
         eng.set_schedule(total, observe=True)
         eng.run()
         status = eng.status()
         frames, hist = eng.frames(with_hist=True)
+        actin = eng.actin_frames() if eng.actin is not None else None
         raw = eng.raw_distances()
         active = eng.counters()["total_active"]
         eng.close()
@@ -119,6 +119,8 @@ def run_condition(driver: str, a: dict, n_chunks: int | None = None, device: int
                 again.append(r)
                 continue
             writers.write_run(a["out"], r, frames[k], hist[k], raw[k], int(active[k]), subfolders=subfolders)
+            if actin is not None:
+                writers.write_actin(a["out"], r, actin[0][k], actin[1][k])
             if not quiet:
                 print(f"Run {r} done ({int((frames[k][:, 8] == 2).sum())} active frames)")
         attempt += 1

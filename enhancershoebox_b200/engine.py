@@ -40,7 +40,20 @@ class ChunkDesc(C.Structure):
                 ("ramp_on", C.c_int), ("ramp_start", C.c_int64), ("ramp_stop", C.c_int64),
                 ("adapt_soft", C.c_int), ("adapt_bond1", C.c_int), ("adapt_bond2", C.c_int),
                 ("observe", C.c_int), ("expected_rnp", C.c_int),
-                ("induce_on", C.c_int), ("activate_on", C.c_int), ("inactivate_on", C.c_int)]
+                ("induce_on", C.c_int), ("activate_on", C.c_int), ("inactivate_on", C.c_int), ("actin_flags", C.c_int)]
+
+
+class ActinParams(C.Structure):
+    _fields_ = [("first", C.c_int), ("count", C.c_int), ("p_nucleation", C.c_double), ("p_on", C.c_double),
+                ("monomer_radius", C.c_double), ("end_radius", C.c_double), ("shell_lo", C.c_double), ("shell_hi", C.c_double),
+                ("adj_min", C.c_double), ("free_box", C.c_double), ("free_min", C.c_double), ("max_tries", C.c_int)]
+
+
+def actin_params(first: int, count: int, p_nucleation: float) -> "ActinParams":
+    """The constants of run_single_shoebox.py:417-418, 428-429, 496, 1001-1004, 1074, 1186-1188, as the reference's own
+    floating-point expressions."""
+    return ActinParams(first, count, float(p_nucleation), P.P_ON, float(P.MONOMER_RADIUS), float(P.FIL_END_RADIUS),
+                       P.SIG_ACTIN - P.W_SA, P.SIG_ACTIN + P.W_SA, (2 ** (1 / 2)) * P.SIG_ACTIN, 1.0, P.SIG_ACTIN, 2000)
 
 
 _lib = None
@@ -55,6 +68,9 @@ _SIGNATURES = {
     "esb_set_coeffs": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "esb_set_fixes": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]),
     "esb_set_neighbor": (C.c_int, [C.c_void_p, C.c_double, C.c_int]),
+    "esb_set_actin": (C.c_int, [C.c_void_p, C.POINTER(ActinParams)]),
+    "esb_get_actin": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 6),
+    "esb_get_actin_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "esb_set_soft": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "esb_set_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                  C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ClosedForm)]),
@@ -163,7 +179,8 @@ class ShoeboxBatch:
 
     def __init__(self, data, n_replicas: int | None = None, driver: str = "genes_stages", condition: str = "Control",
                  device: int = 0, table_file: str | None = None, seeds=None, thresholds=None, activations=None,
-                 langevin_mode: int = 1, neigh_skin: float = P.NEIGH_SKIN, neigh_delay: int = P.NEIGH_DELAY):
+                 langevin_mode: int = 1, neigh_skin: float = P.NEIGH_SKIN, neigh_delay: int = P.NEIGH_DELAY,
+                 p_nucleation: float | None = None):
         """`data`: one ShoeboxData (copied to all replicas) or a list with one per replica (same
         topology).  `thresholds` = -x values, `activations` = -a values (per mille, as on the CLI)."""
         self.lib = load_library()
@@ -191,6 +208,16 @@ class ShoeboxBatch:
         br = np.array([0.0, P.BOND_R0[1], P.BOND_R0[2]])
         ak = np.array([0.0, P.ANGLE_K[1], P.ANGLE_K[2]])
         self._check(self.lib.esb_set_coeffs(self.h, _dp(bk), _dp(br), _dp(ak)))
+        # actin polymerisation events (run_single_shoebox.py:969-1298): every condition of the actin driver but the
+        # static-topology ones (:459-460)
+        self.actin = None
+        actin_ids = np.flatnonzero(np.asarray(d0.types) == P.ACTIN_TYPE)
+        if p_nucleation is not None and len(actin_ids) and condition not in P.STATIC_ACTIN_CONDITIONS:
+            first, count = int(actin_ids[0]), len(actin_ids)
+            if not np.array_equal(actin_ids, np.arange(first, first + count)):
+                raise ValueError("actin beads must be one contiguous block of atom ids")
+            self.actin = actin_params(first, count, p_nucleation)
+            self._check(self.lib.esb_set_actin(self.h, C.byref(self.actin)))
         self._check(self.lib.esb_set_fixes(self.h, P.DT, P.LANGEVIN_T, P.LANGEVIN_DAMP, langevin_mode, P.WALL_EPS, P.WALL_CUT))
         if "ESB_SKIN" not in os.environ and "ESB_DELAY" not in os.environ:          # (perf experiments override through the environment)
             self._check(self.lib.esb_set_neighbor(self.h, float(neigh_skin), int(neigh_delay)))
@@ -296,6 +323,7 @@ class ShoeboxBatch:
             d.induce_on = int(i >= P.T_INDUCTION_ON)
             d.activate_on = int(P.T_INDUCTION_ON <= i < t_act_off)
             d.inactivate_on = int(i >= P.T_INDUCTION_ON)
+            d.actin_flags = P.actin_flags(i, self.condition) if self.actin is not None else 0
         self._check(self.lib.esb_set_schedule(self.h, len(plans), descs))
         self.n_chunks = len(plans)
         self.plans = list(plans)
@@ -332,6 +360,35 @@ class ShoeboxBatch:
         out = np.empty((self.R, n, 2))
         self._check(self.lib.esb_get_raw_distances(self.h, chunk_begin, n, _dp(out)))
         return out
+
+    def actin_state(self):
+        """Filament bookkeeping per replica: dict(plus, minus [R, count] neighbour atom ids (-1 none), free = list of
+        free_actin lists, filaments = list of filament_details lists (plus end first))."""
+        n = self.actin.count
+        plus, minus = np.empty((self.R, n), np.int32), np.empty((self.R, n), np.int32)
+        fl, fp = np.empty((self.R, n), np.int32), np.empty((self.R, n), np.int32)
+        nfree, nfil = np.empty(self.R, np.int32), np.empty(self.R, np.int32)
+        self._check(self.lib.esb_get_actin(self.h, _ip(plus), _ip(minus), _ip(nfree), _ip(fl), _ip(nfil), _ip(fp)))
+        first = self.actin.first
+        free = [list(fl[r, :nfree[r]]) for r in range(self.R)]
+        fils = []
+        for r in range(self.R):
+            out = []
+            for b in fp[r, :nfil[r]]:
+                chain = [int(b)]
+                while minus[r, chain[-1] - first] >= 0:
+                    chain.append(int(minus[r, chain[-1] - first]))
+                out.append(chain)
+            fils.append(out)
+        return dict(plus=plus, minus=minus, free=free, filaments=fils)
+
+    def actin_frames(self, chunk_begin: int = 0, n_chunks: int | None = None):
+        """(stats [R, n, 6] = n_filaments, sum len, sum len^2, n_free, min len, max len; hist [R, n, 49])."""
+        n = self.n_chunks - chunk_begin if n_chunks is None else n_chunks
+        stats = np.empty((self.R, n, 6), np.int32)
+        hist = np.empty((self.R, n, 49), np.int32)
+        self._check(self.lib.esb_get_actin_frames(self.h, chunk_begin, n, _ip(stats), _ip(hist)))
+        return stats, hist
 
     def status(self):
         st = np.empty(self.R, np.int32)

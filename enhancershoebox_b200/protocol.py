@@ -52,6 +52,29 @@ ANGLE_K = {1: 100 / SIG_CHROMATIN_NM, 2: 33.0}
 SOFT_A_RAMP = (0.0, 60.0)
 TABLE_LENGTH = 30000  # pair_style table lookup 30000
 
+# actin dynamics (run_single_shoebox.py:398-423, 456-466, 489-496)
+ACTIN_TYPE = 3
+FILAMENT_LENGTH = 3
+T_POLYMERIZATION_ON = 40
+T_ON_PLUS = 1
+T_ON_MINUS = 40
+T_OFF_MINUS = 5
+P_ON = 0.3
+SIG_ACTIN = 0.3
+W_SA = 0.2
+FIL_END_RADIUS = 3
+MONOMER_RADIUS = 2
+STATIC_ACTIN_CONDITIONS = ("LatB", "SwinA_nopol")            # t_polymerization_on = 2*NRuns (:459-460)
+
+
+def actin_flags(i: int, condition: str = "Control") -> int:
+    """Which actin events Python timestep i performs (run_single_shoebox.py:969, 1064, 1101, 1168):
+    1 = nucleation + plus-end polymerisation, 2 = minus-end polymerisation, 4 = minus-end depolymerisation."""
+    if condition in STATIC_ACTIN_CONDITIONS or (i + 1) < T_POLYMERIZATION_ON:
+        return 0
+    return 1 | (2 if i % (T_ON_PLUS * T_ON_MINUS) == 0 else 0) | (4 if i % T_OFF_MINUS == 0 else 0)
+
+
 TREATMENT_DURATION = {  # run_single_shoebox.py:379-385
     "Hexanediol": int(3 * 60 / 0.6), "JQ-1": int(30 * 60 / 0.6), "Flavopiridol": int(30 * 60 / 0.6),
 }

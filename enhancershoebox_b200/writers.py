@@ -62,6 +62,31 @@ def event_log(states: np.ndarray) -> list:
     return ev
 
 
+def actin_track_lines(stats: np.ndarray):
+    """actinTrack.txt rows (run_single_shoebox.py:1544): t, n_filaments, round(mean length, 2), round(sd, 2), n_free,
+    tab separated.  stats [n, 6] = n_filaments, sum len, sum len^2, n_free, min, max; mean/sd are np.mean / np.std of
+    the integer lengths, recomputed here from the two sums (equal to the reference's values after the rounding to 2
+    decimals except when the third decimal sits on a rounding boundary)."""
+    for i, (nf, s1, s2, nfree, _, _) in enumerate(np.asarray(stats, np.int64)):
+        if nf > 0:
+            mean = float(s1) / float(nf)
+            sd = float(np.sqrt(max(float(s2) / float(nf) - mean * mean, 0.0)))
+        else:
+            mean = sd = float("nan")
+        yield str((i + 1) * P.DELT) + "\t" + str(int(nf)) + "\t" + str(round(mean, 2)) + "\t" + str(round(sd, 2)) + "\t" + str(int(nfree)) + "\n"
+
+
+def write_actin(out_folder: str, run_number: int, stats: np.ndarray, hist: np.ndarray) -> None:
+    """actinTrack.txt and actinAroundCluster.txt of one repeat (run_single_shoebox.py:738-756, 1544, 1581-1590)."""
+    run_dir = os.path.join(out_folder, "run" + str(run_number))
+    with open(os.path.join(run_dir, "actinTrack.txt"), "w") as f:
+        f.writelines(actin_track_lines(stats))
+    with open(os.path.join(run_dir, "actinAroundCluster.txt"), "w") as f:
+        f.write(cluster_header())
+        for i in range(len(stats)):
+            f.write(str((i + 1) * P.DELT) + "," + ",".join(str(int(v)) for v in hist[i]) + "\n")
+
+
 def write_run(out_folder: str, run_number: int, frames: np.ndarray, hist: np.ndarray, raw: np.ndarray, total_active_steps: int,
               n_runs: int = P.N_RUNS, subfolders=("figures", "image_files", "microscopy_files")) -> None:
     """Everything one repeat leaves on disk.  frames [n,9], hist [n,49], raw [n,2] = (d_rp, d_rg) in bead units."""

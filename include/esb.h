@@ -73,7 +73,36 @@ typedef struct {
     int induce_on;          /* i >= t_induction_on and i < t_induction_off                    (:1304)      */
     int activate_on;        /* i >= t_activation_on and i < t_activation_off (Flavopiridol: off from NRuns, :885-886, 1322) */
     int inactivate_on;      /* i >= t_activation_on                                           (:1380)      */
+    int actin_flags;        /* actin events of this chunk (run_single_shoebox.py:969-1298): 1 = nucleation + plus-end
+                             * polymerisation ((i+1) >= t_polymerization_on), 2 = minus-end polymerisation
+                             * (i % (t_on_plus*t_on_minus) == 0), 4 = minus-end depolymerisation (i % t_off_minus == 0) */
 } esb_chunk_desc;
+
+/* Actin polymerisation dynamics (run_single_shoebox.py:398-423, 489-496, 969-1298).  Actin beads are the atoms
+ * [first, first+count) (0-based, all of type 3); bonds/angles of type 2 among them given to esb_set_topology()
+ * are the initial filaments (make_input_file.py:83-87; the lower atom id is the plus end, :540-553).  With this
+ * call bonds, angles and the 1-2/1-3/1-4 exclusions of the actin beads become per-replica state that the
+ * per-chunk events rewrite (create_bonds single/bond 2, single/angle 2, delete_bonds ... remove special). */
+typedef struct {
+    int first, count;
+    double p_nucleation;        /* -n                                                   (:300, 981)  */
+    double p_on;                /* pon = 0.3                                            (:496)       */
+    double monomer_radius;      /* monomerEffectRadius = 2                              (:418)       */
+    double end_radius;          /* filEndEffectRadius = 3                               (:417)       */
+    double shell_lo, shell_hi;  /* sig_actin - w_sa, sig_actin + w_sa                   (:428-429, 1001-1003) */
+    double adj_min;             /* 2**(1/2) * sig_actin: distance to the adjacent bead  (:1074)      */
+    double free_box;            /* 1: half edge of the cube a released monomer is placed in (:1186)  */
+    double free_min;            /* sig_actin: its minimal distance to the old neighbour (:1188)      */
+    int max_tries;              /* 2000                                                 (:1004)      */
+} esb_actin_params;
+int esb_set_actin(esb_handle *h, const esb_actin_params *p);
+/* Filament bookkeeping of every replica after the last run: plus[R][count], minus[R][count] = neighbour of each
+ * actin bead towards the plus / minus end (atom id, -1 none); n_free[R], free_list[R][count] = free_actin in list
+ * order; n_fil[R], fil_plus[R][count] = plus-end atom of every filament in filament_details order. */
+int esb_get_actin(esb_handle *h, int *plus, int *minus, int *n_free, int *free_list, int *n_fil, int *fil_plus);
+/* actinTrack.txt / actinAroundCluster.txt rows (:1523-1544): stats [R][n_chunks][6] = n_filaments, sum of lengths,
+ * sum of squared lengths, n_free_actin, min and max length; hist [R][n_chunks][49] or NULL. */
+int esb_get_actin_frames(esb_handle *h, int chunk_begin, int n_chunks, int *stats, int *hist);
 
 const char *esb_last_error(void);
 int esb_version(void);
