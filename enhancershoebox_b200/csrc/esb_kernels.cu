@@ -465,7 +465,8 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
             const float4 pi = S.pos[i];
 #pragma unroll 1
             for (int t = 0; t < ESB_MAX_TERMS; t++) {
-                const uint2 term = __ldcg(&bterm[(size_t)t * ntp + i]);      // (another SM may have rewritten it one chunk ago)
+                // (with actin dynamics another SM may have rewritten the row one chunk ago: bypass L1 then)
+                const uint2 term = a.bterm_stride ? __ldcg(&bterm[(size_t)t * ntp + i]) : bterm[(size_t)t * ntp + i];
                 const int kind = term.y & 0xff, type = (term.y >> 8) & 0xff;
                 if (kind == 0) break;                                         // a bead's terms are stored without gaps
                 const float4 pa = S.pos[term.x & 0xffffu];
