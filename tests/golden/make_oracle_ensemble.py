@@ -1,7 +1,9 @@
 """Generates tests/golden/oracle_ensemble_box11.npz: per-chunk ensemble statistics of the CPU oracle
 (box 11, promoter 3, threshold 20, activation 100/1000) over N replicas x 400 chunks.
 Run here (CPU): python tests/golden/make_oracle_ensemble.py <first_replica> <n_replicas> <out.npz>
-then merge with --merge.  Used by tests/test_gpu_ensemble.py as the statistical reference."""
+then merge with --merge.  Used by tests/test_gpu_ensemble.py as the statistical reference.
+(Regenerated with the oracle's `neigh_modify delay 10` rule: 8 x `make_oracle_ensemble.py 6k 6 part_k.npz`, then
+`--merge oracle_ensemble_box11.npz part_*.npz`.)"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
@@ -42,7 +44,12 @@ def run(first, count, out):
 if __name__ == '__main__':
     if sys.argv[1] == '--merge':
         parts = [np.load(p) for p in sys.argv[3:]]
-        np.savez_compressed(sys.argv[2], **{k: np.concatenate([p[k] for p in parts]) for k in ('frames', 'ke', 'nrnp', 'status')},
+        fr = np.concatenate([p['frames'] for p in parts])
+        cat = lambda k: np.concatenate([p[k] for p in parts])
+        # compact form read by tests/test_gpu_ensemble.py (only the columns the test compares)
+        np.savez_compressed(sys.argv[2], d_rp=fr[:, :, 4].astype(np.float32), d_rg=fr[:, :, 5].astype(np.float32),
+                            n_prom=fr[:, :, 6].astype(np.int16), n_gene=fr[:, :, 7].astype(np.int16), state=fr[:, :, 8].astype(np.int8),
+                            ke=cat('ke').astype(np.float32), nrnp=cat('nrnp').astype(np.int16), status=cat('status'),
                             meta=np.array([NCH, THR, ACT]))
     else:
         run(int(sys.argv[1]), int(sys.argv[2]), sys.argv[3])
