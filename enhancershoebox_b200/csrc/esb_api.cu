@@ -862,7 +862,7 @@ static int prepare_launch(esb_handle *h, size_t *smem)
         int rc = rebuild_setups(h);
         if (rc) return rc;
     }
-    *smem = esb_smem_bytes(h->n_pad, (int)h->tables.size());
+    *smem = esb_smem_bytes_v512(h->n_pad, (int)h->tables.size());
     if (*smem > 227 * 1024) return fail(ESB_EINVAL, "replica of %d atoms needs %zu B of shared memory (max 232448)", h->N, *smem);
     return ESB_OK;
 }
@@ -879,7 +879,14 @@ int esb_run(esb_handle *h, int chunk_begin, int n_chunks, void *stream)
     if (rc) return rc;
     KArgs k;
     fill_kargs(h, k, false);
-    CK(esb_launch_run(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem, (cudaStream_t)stream, h->d_sched, h->n_sm));
+    // a batch that cannot fill the device with two CTAs per SM gets the 32-warp CTA: a replica then advances twice as fast
+    const bool wide = getenv("ESB_WIDE") ? atoi(getenv("ESB_WIDE")) != 0 : h->R <= h->n_sm;
+    if (wide) {
+        const size_t smem_w = esb_smem_bytes_v1024(h->n_pad, (int)h->tables.size());
+        CK(esb_launch_run_v1024(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem_w, (cudaStream_t)stream, h->d_sched, h->n_sm));
+    } else {
+        CK(esb_launch_run_v512(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem, (cudaStream_t)stream, h->d_sched, h->n_sm));
+    }
     return ESB_OK;
 }
 

@@ -13,7 +13,7 @@
 #define ESB_THREADS 512
 #endif
 #ifndef ESB_PREFETCH
-#define ESB_PREFETCH 4                  // neighbour-list entries each lane keeps in flight (even)
+#define ESB_PREFETCH 2                  // neighbour-list entries each lane keeps in flight (even); 2 is best with 16-warp CTAs
 #endif
 #ifndef ESB_MIN_CTAS
 #define ESB_MIN_CTAS 2                  // resident CTAs per SM the step kernel is compiled for (2 x 16 warps: 64 registers)
@@ -143,8 +143,20 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // u32 -> uniform in [-0.5, 0.5]; identical to the oracle's u32_to_centered.
 __device__ __forceinline__ float u32_centered(uint32_t u) { return (float)(int32_t)u * 0x1p-32f; }
 
-size_t esb_smem_bytes(int n_pad, int n_tables);
-cudaError_t esb_launch_run(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
-                           int *sched, int n_sm);
+// esb_kernels.cu is compiled twice into libesb.so: ESB_TAG 512 = 16-warp CTAs, two per SM (full batches), and
+// ESB_TAG 1024 = 32-warp CTAs, one per SM, which steps a replica twice as fast and is chosen when the batch has
+// no more replicas than the device has SMs (e.g. configs[1]: 64 actin seeds on one GPU).
+#ifndef ESB_TAG
+#define ESB_TAG 512
+#endif
+#define ESB_CAT2_(a, b) a##b
+#define ESB_CAT2(a, b) ESB_CAT2_(a, b)
+#define ESB_VARIANT(name) ESB_CAT2(name##_v, ESB_TAG)
+size_t esb_smem_bytes_v512(int n_pad, int n_tables);
+size_t esb_smem_bytes_v1024(int n_pad, int n_tables);
+cudaError_t esb_launch_run_v512(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
+                                int *sched, int n_sm);
+cudaError_t esb_launch_run_v1024(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
+                                 int *sched, int n_sm);
 cudaError_t esb_launch_forces(const KArgs &k, int pair_mode, int setup_id, float soft_a, int with_post, unsigned long long eval,
                               double *f_out, double *e_out, size_t smem, cudaStream_t st);

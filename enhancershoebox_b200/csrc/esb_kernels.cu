@@ -1130,6 +1130,8 @@ __device__ __noinline__ void actin_events(const KArgs &a, const int r, const esb
 // advance in a ring and no SM idles while another still has a queue (a plain grid of R CTAs would
 // leave 148*3 - (R mod 148*3) slots empty for the whole last wave).  The grid never exceeds the
 // number of co-resident CTAs, so a waiting CTA's producer is always running.
+// (own namespace per compiled variant: the two instantiations must not be merged by the linker)
+namespace ESB_VARIANT(esb_step) {
 template <int NP>
 __global__ void __launch_bounds__(ESB_THREADS, ESB_MIN_CTAS)
 esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int n_chunks, const double delt, const double sig_nm,
@@ -1254,6 +1256,10 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
     }
 }
 
+}  // namespace esb_step_v*
+using ESB_VARIANT(esb_step)::esb_run_kernel;
+
+#if ESB_TAG == 512
 // Parity hook: one force evaluation at the stored positions (esb_forces()).
 template <int NP>
 __global__ void __launch_bounds__(ESB_THREADS, 2)
@@ -1339,7 +1345,9 @@ extern "C" __global__ void esb_unpack_kernel(const float4 *pos4, const float4 *v
     }
 }
 
-size_t esb_smem_bytes(int n_pad, int n_tables) { return smem_bytes_for(n_pad, n_tables); }
+#endif   // ESB_TAG == 512 (parity hook and the pack/unpack kernels exist once)
+
+size_t ESB_VARIANT(esb_smem_bytes)(int n_pad, int n_tables) { return smem_bytes_for(n_pad, n_tables); }
 
 // Host launchers: the kernels are instantiated for the bead capacities of the reference's box sizes
 // (box 9..12 without actin: 1050/1172/1290/1400 beads -> 1056/1184/1312/1408; box 11 with actin:
@@ -1355,8 +1363,8 @@ size_t esb_smem_bytes(int n_pad, int n_tables) { return smem_bytes_for(n_pad, n_
         default: { constexpr int NPC = 0; __VA_ARGS__; break; }      \
     }
 
-cudaError_t esb_launch_run(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
-                           int *sched /* [1 + n_replicas] device ints: ticket, progress[] */, int n_sm)
+cudaError_t ESB_VARIANT(esb_launch_run)(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
+                                        int *sched /* [1 + n_replicas] device ints: ticket, progress[] */, int n_sm)
 {
     cudaError_t e = cudaSuccess;
     ESB_FOR_NP(k.n_pad, {
@@ -1374,6 +1382,7 @@ cudaError_t esb_launch_run(const KArgs &k, int chunk_begin, int n_chunks, double
     return e;
 }
 
+#if ESB_TAG == 512
 cudaError_t esb_launch_forces(const KArgs &k, int pair_mode, int setup_id, float soft_a, int with_post, unsigned long long eval,
                               double *f_out, double *e_out, size_t smem, cudaStream_t st)
 {
@@ -1387,3 +1396,4 @@ cudaError_t esb_launch_forces(const KArgs &k, int pair_mode, int setup_id, float
     })
     return e;
 }
+#endif
