@@ -34,7 +34,6 @@ struct Smem {
 
 enum { M_QCTR = 0 /* next quad of the running build / force loop */, M_FAIL, M_PAIRS, M_CURLIST, M_SCAN /* one per warp */,
        M_CNT_PROM = M_SCAN + ESB_THREADS / 32, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */, M_END = M_HIST + 52 };
-static_assert((ESB_NL_MAXNB + 1) % ESB_THREADS == 0, "length-sort scan: equal share of counters per thread");
 enum { D_RR = 0, D_PROBE = 3, D_GENE = 6, D_END = 10 };
 
 __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables)
@@ -421,10 +420,10 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         for (int k = tid; k < n; k += ESB_THREADS) atomicAdd(&hist[ESB_NL_MAXNB - (int)(qbuild[k].y >> 16)], 1);
         __syncthreads();
         // exclusive scan of the 1024 counters: an equal share per thread
-        constexpr int PER = (ESB_NL_MAXNB + 1) / ESB_THREADS;
+        constexpr int PER = (ESB_NL_MAXNB + ESB_THREADS) / ESB_THREADS;
         int v[PER], s = 0;
 #pragma unroll
-        for (int k = 0; k < PER; k++) { v[k] = hist[PER * tid + k]; s += v[k]; }
+        for (int k = 0; k < PER; k++) { v[k] = (PER * tid + k <= ESB_NL_MAXNB) ? hist[PER * tid + k] : 0; s += v[k]; }
         int incl = s;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -436,7 +435,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         int base = incl - s;
         for (int w = 0; w < warp; w++) base += S.misc[M_SCAN + w];
 #pragma unroll
-        for (int k = 0; k < PER; k++) { hist[PER * tid + k] = base; base += v[k]; }
+        for (int k = 0; k < PER; k++) { if (PER * tid + k <= ESB_NL_MAXNB) hist[PER * tid + k] = base; base += v[k]; }
         __syncthreads();
         for (int k = tid; k < n; k += ESB_THREADS) {
             const uint2 d = qbuild[k];

@@ -62,3 +62,80 @@ def gather_rows(local: np.ndarray, n_total: int, group=None, device=None) -> np.
     parts = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(parts, t, group=group)
     return np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)], axis=0)
+
+
+def sweep_groups(promoters, activations, thresholds, repeats: int, group: int = 5):
+    """(promoter, threshold, activation, first_repeat) of every `group`-run block of the sweep, in the aggregator's
+    loop order (VisitorGeneMaps/dist_genestages_grouped.py:45-54, 70-106): one output row each."""
+    out = []
+    for p in promoters:
+        for a in activations:
+            for t in thresholds:
+                for g in range(repeats // group):
+                    out.append((p, t, a, 1 + g * group))
+    return out
+
+
+def run_sweep(box: int, promoters=(1, 2, 3), activations=(30,), thresholds=(10, 20, 30, 40, 50, 60, 70, 80, 90, 100),
+              repeats: int = 5, n_chunks: int | None = None, group: int = 5, batch_groups: int = 118, device: int = 0,
+              seed_base: int = 0, retries: int = 3, progress=None):
+    """The GENE_STAGES sweep (VisitorGeneMaps/run_singleCond_parallel.sh + dist_genestages_grouped.py) without the
+    filesystem in between: the 5-run groups are dealt to the ranks (one process per GPU, no collective on the step
+    path), every rank runs its groups as batches of replicas, reduces each group's geneTrack records to the summary
+    row ON the device (the frames never leave HBM) and the rows are all-gathered at the end.
+
+    Returns (groups, rows): groups = sweep_groups(...) and rows [len(groups), 4] = S5PInt, S2PInt, Contact,
+    DistActivation on every rank.  A replica that dies (status != 0; LAMMPS would have aborted that run) is redone
+    with a fresh seed, as the reference's launcher does (run_parallel_shoebox.sh:1-14)."""
+    import ctypes as C
+
+    import torch.distributed as dist
+
+    from . import datafile, engine as E, protocol as P
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    groups = sweep_groups(promoters, activations, thresholds, repeats, group)
+    lo, hi = shard_range(len(groups), rank, world)
+    mine = list(range(lo, hi))
+    rows = np.full((hi - lo, 4), np.nan)
+    total = P.N_RUNS if n_chunks is None else n_chunks
+    lib = E.load_library()
+    attempt = {g: 0 for g in mine}
+    for p in promoters:
+        pending = [g for g in mine if groups[g][0] == p]
+        while pending:
+            now, pending = pending[:batch_groups], pending[batch_groups:]
+            runs = [(g, k) for g in now for k in range(group)]
+            seeds = np.array([seed_base + 1_000_003 * attempt[g] + (g * group + k) + 1 for g, k in runs], dtype=np.uint64)
+            datas = [datafile.make_shoebox(box, p, False, seed=int(s)) for s in seeds]
+            eng = E.ShoeboxBatch(datas, seeds=seeds, thresholds=[groups[g][1] for g, _ in runs],
+                                 activations=[groups[g][2] for g, _ in runs], device=device)
+            eng.set_schedule(total, observe=True)
+            eng.run()
+            ok = (eng.status() == 0).reshape(len(now), group).all(axis=1)
+            out = np.empty((len(now), 4))
+            rc = lib.esb_aggregate_grouped(device, C.c_void_p(eng.device_ptr(2)), 1, len(runs), total, group, 250.0, P.T_INDUCTION_ON,
+                                           out.ctypes.data_as(C.POINTER(C.c_double)), None)
+            eng.close()
+            if rc != 0:
+                raise E.EsbError(f"esb_aggregate_grouped failed with {rc}")
+            for q, g in enumerate(now):
+                if ok[q]:
+                    rows[g - lo] = out[q]
+                elif attempt[g] < retries:
+                    attempt[g] += 1
+                    pending.append(g)
+            if progress:
+                progress(rank, p, len(now), len(pending))
+    return groups, gather_rows(rows, len(groups))
+
+
+def summary_csv(groups, rows) -> str:
+    """summary_contact_grouped_*.txt as `df_summary.to_csv` writes it (VisitorGeneMaps/dist_genestages_grouped.py:101-111)."""
+    import pandas as pd
+    cols = ['Promoter', 'Threshold', 'Activation', 'S5PInt', 'S2PInt', 'Contact', 'DistActivation']
+    df = pd.DataFrame(columns=cols)
+    parts = [pd.DataFrame(data=np.array([[p, t, a, r[0], r[1], r[2], r[3]]], dtype=object), columns=cols) for (p, t, a, _), r in zip(groups, rows)]
+    if parts:
+        df = pd.concat([df] + parts, ignore_index=True)
+    return df.to_csv()

@@ -1,6 +1,4 @@
 cd /root/repo
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-ESB_WIDE=0 timeout 200 python scripts/perf_actin.py 64 80
-ESB_WIDE=1 timeout 200 python scripts/perf_actin.py 64 80
-timeout 200 python scripts/perf_actin.py 148 80
-timeout 120 python scripts/perf12.py 592 6 v512
+timeout 600 python -m pytest tests/test_gpu_sweep.py -x -q 2>&1 | tail -8
+timeout 600 python run_sweep.py -b 12 --promoters 3 --activations 30 --thresholds 10 20 30 40 50 60 70 80 90 100 --repeats 55 -t 400 -o gpurun_out/sweep_box12.txt 2>&1 | tail -5
+head -5 gpurun_out/sweep_box12.txt

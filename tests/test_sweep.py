@@ -56,3 +56,16 @@ def test_gather_rows_gloo_world2():
     exp = np.arange(n_total, dtype=np.float64)[:, None] * np.array([1.0, 10.0, 100.0, np.nan])[None, :]
     for r in range(2):
         assert np.array_equal(got[r], exp, equal_nan=True)
+
+
+def test_sweep_groups_and_summary_format():
+    g = sweep.sweep_groups((1, 2, 3), (1, 5, 10, 15, 20, 25, 30, 50, 75, 100), (10, 20, 30, 40, 50, 60, 70, 75, 80, 90, 100), 100)
+    assert len(g) == 6600 and g[0] == (1, 10, 1, 1) and g[19] == (1, 10, 1, 96) and g[20] == (1, 20, 1, 1)      # rows of summary_contact_grouped_*.txt
+    csv = sweep.summary_csv(g[:2], np.array([[59.5, 0.0, 23.975, np.nan], [60.25, 8.426395939086294, 24.0, 452.8204550361811]]))
+    assert csv.splitlines() == [",Promoter,Threshold,Activation,S5PInt,S2PInt,Contact,DistActivation",
+                                "0,1,10,1,59.5,0.0,23.975,", "1,1,10,1,60.25,8.426395939086294,24.0,452.8204550361811"]
+    path = "/root/reference/VisitorGeneMaps/summary_contact_grouped_Thresholds10-100.txt"
+    if os.path.exists(path):                       # same header and row labels as the shipped table
+        ref = open(path).read().splitlines()
+        assert ref[0] == csv.splitlines()[0] and len(ref) == 1 + 6600
+        assert [r.split(",")[:4] for r in ref[1:21]] == [[str(k), "1", "10", "1"] for k in range(20)]
