@@ -1,4 +1,7 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_gpu_sweep.py -x -q 2>&1 | tail -8
-timeout 600 python run_sweep.py -b 12 --promoters 3 --activations 30 --thresholds 10 20 30 40 50 60 70 80 90 100 --repeats 55 -t 400 -o gpurun_out/sweep_box12.txt 2>&1 | tail -5
-head -5 gpurun_out/sweep_box12.txt
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py > gpurun_out/bench_s2c.log 2>&1; tail -1 gpurun_out/bench_s2c.log
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -1 gpurun_out/bench_ref.log
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_s2_short.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1c_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_ll.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:esb_run_kernel --launch-skip 1 --launch-count 1 -f -o gpurun_out/prof_r1c_bench python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
