@@ -44,6 +44,32 @@ def test_random_frames_against_numpy_restatement(n_runs, n_frames):
     assert out.shape == (n_runs // 5, 4) and np.array_equal(out, ref, equal_nan=True)
 
 
+def test_config5_256_runs_of_10000_frames():
+    """configs[4]: the analysis alone on 256 runs x 1e4 frames (synthetic frames as SURVEY 8d: d_rp, d_rg ~ U(50, 900) nm,
+    s5p ~ randint(0, 120), a 3-state script), bit-exact against the Python statements of the reference script."""
+    import time
+    rng = np.random.default_rng(0)
+    n_runs, n_frames = 256, 10000
+    fr = np.zeros((n_runs, n_frames, 9))
+    fr[:, :, 4] = rng.uniform(50, 900, (n_runs, n_frames))
+    fr[:, :, 5] = rng.uniform(50, 900, (n_runs, n_frames))
+    fr[:, :, 6] = rng.integers(0, 120, (n_runs, n_frames))
+    state = np.zeros((n_runs, n_frames), np.int64)
+    for r in range(n_runs):                                   # inactive -> induced at 150 -> bursts of 50 active frames
+        state[r, 150:] = 1
+        for start in rng.integers(160, n_frames - 60, rng.integers(0, 12)):
+            state[r, start:start + 50] = 2
+    fr[:, :, 8] = state
+    t0 = time.time()
+    out = E.aggregate_grouped(fr)
+    t_gpu = time.time() - t0
+    ref = AGG.grouped(fr)
+    assert out.shape == (51, 4) and np.array_equal(out, ref, equal_nan=True)
+    rows = E.aggregate_runs(fr)
+    assert np.array_equal(rows, AGG.per_run_percentile(fr), equal_nan=True)
+    print(f"256 x 1e4 frames: {t_gpu * 1e3:.1f} ms incl. the 184 MB host->device copy")
+
+
 def test_ragged_and_empty_cases():
     fr = np.zeros((5, 400, 9))
     fr[:, :, 4] = 300.0                                     # never in contact, never active
