@@ -152,3 +152,48 @@ def test_neighbour_delay_semantics(oracle_lib, box11, pair_tables, oracle_lookup
     assert 2 <= c10["builds"] <= 1 + 200 // 10                     # set-up + at most one per 10 steps
     assert c0["builds"] > c10["builds"] and c0["dangerous"] == 0
     assert 0 < c10["dangerous"] <= c10["builds"] - 1
+
+
+def test_lookup_table_against_scipy_cubic_spline(oracle_lib, sections):
+    """The table construction ([LAMMPS-ext] PairTable::read_table with RSQ, spline_table, compute_table) restated with a
+    third-party spline: scipy's CubicSpline with clamped ends is the same interpolant as LAMMPS' spline()/splint()
+    (Numerical Recipes).  End slopes: E' = -F at both ends, F' by finite differences of the first / last two file rows."""
+    from scipy.interpolate import CubicSpline
+    for key, cut in (("SER5P_SER5P", 0.9), ("RNP_RNP_ATTRACTION", 2.9), ("CHROMATIN_CHROMATIN", 1.2)):
+        sec = sections[key]
+        n, rlo, rhi = int(sec.n), float(sec.rlo), float(sec.rhi)
+        ef, ff = np.asarray(sec.e, np.float64), np.asarray(sec.f, np.float64)
+        r = np.sqrt(rlo * rlo + (rhi * rhi - rlo * rlo) * np.arange(n) / (n - 1))       # RSQ: file r values are regenerated
+        e_spl = CubicSpline(r, ef, bc_type=((1, -ff[0]), (1, -ff[-1])))
+        f_spl = CubicSpline(r, ff, bc_type=((1, (ff[1] - ff[0]) / (r[1] - r[0])), (1, (ff[-1] - ff[-2]) / (r[-1] - r[-2]))))
+        e, f, inner, delta = oracle_lib.build_lookup_table(sec, cut)
+        assert inner == rlo * rlo and abs(delta - (cut * cut - inner) / 29999) < 1e-18
+        rm = np.sqrt(inner + (np.arange(29999) + 0.5) * delta)                          # bin midpoints in r
+        e_ref, f_ref = e_spl(rm), f_spl(rm) / rm
+        assert np.max(np.abs(e - e_ref) / (1 + np.abs(e_ref))) < 1e-9, key
+        assert np.max(np.abs(f - f_ref) / (1 + np.abs(f_ref))) < 1e-9, key
+
+
+def test_nve_conserves_energy_without_thermostat(oracle_lib, box11, pair_tables, oracle_lookup, snapshots):
+    """fix nve alone (langevin off, constant soft prefactor, no fix adapt): velocity-Verlet with forces that are the
+    gradient of the reported energies (pair soft + bonds + angles + walls) conserves E_pot + E_kin to O(dt^2) --
+    an integrator/force-consistency check that does not depend on LAMMPS."""
+    x, v, t = snapshots["x9"].astype(np.float64), snapshots["v9"].astype(np.float64), snapshots["t9"].astype(np.int32)
+    o = oracle_lib.Oracle(box11, pair_tables, oracle_lookup, seed=3)
+    o.set_langevin(0)
+    o.set_state(t, x, v)
+    o.set_pair("soft")
+    o.L.esbo_pair_soft(o.h, 54.0, oracle_lib._dp(o.soft_cut))
+    o.L.esbo_clear_adapt(o.h)
+
+    def energies():
+        _, e, st = o.forces(with_post=True)
+        _, vv, _, _ = o.state()
+        return st, e.sum() + 0.5 * (vv ** 2).sum(), 0.5 * (vv ** 2).sum()
+
+    st, e0, ke0 = energies()
+    assert st == 0 and ke0 > 1000
+    for _ in range(4):
+        assert o.run(50) == 0
+        st, e1, _ = energies()
+        assert st == 0 and abs(e1 - e0) < 2e-3 * ke0, (e0, e1)
