@@ -727,11 +727,13 @@ __device__ __noinline__ int atom_phase(const KArgs &a, const bool do_final, cons
     return flags;
 }
 
-// [LAMMPS-ext] Variable ramp(x,y) = x + (y-x)*(step-start)/(stop-start), evaluated by fix adapt
-// at set-up and every nevery steps (run_single_shoebox.py:627-639).
+// [LAMMPS-ext] Variable ramp(x,y): delta = step - start; if (delta != 0) delta /= stop - start; x + delta*(y-x),
+// evaluated by fix adapt at set-up and every nevery steps (run_single_shoebox.py:627-639); `run 0` gives x.
 __device__ __forceinline__ double ramp(const double v0, const double v1, long long step, long long rb, long long re)
 {
-    return v0 + (v1 - v0) * (double)(step - rb) / (double)(re - rb);
+    double delta = (double)(step - rb);
+    if (delta != 0.0) delta /= (double)(re - rb);
+    return v0 + delta * (v1 - v0);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -658,8 +658,11 @@ static void apply_adapt(esbo_system *s, long long beginstep, long long endstep, 
             if (a->nevery == 0) continue;
             if (s->step % a->nevery) continue;
         }
-        /* [LAMMPS-ext] Variable ramp(x,y) = x + (y-x)*(step-begin)/(end-begin) */
-        const double val = a->v0 + (a->v1 - a->v0) * (double)(s->step - beginstep) / (double)(endstep - beginstep);
+        /* [LAMMPS-ext] Variable ramp(x,y): delta = step - begin; if (delta != 0) delta /= end - begin;
+         * value = x + delta*(y-x)  (so `run 0` evaluates to x instead of 0/0) */
+        double delta = (double)(s->step - beginstep);
+        if (delta != 0.0) delta /= (double)(endstep - beginstep);
+        const double val = a->v0 + delta * (a->v1 - a->v0);
         if (a->kind == 0) s->soft_a = val;
         else s->bond_r0[a->index] = val;
     }
