@@ -181,7 +181,10 @@ def run_native(args, w):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B.build()
+    if local == 0:
+        B.build()                                  # no-op when libesb.so is newer than its sources; never by two ranks at once
+    if world > 1:
+        dist.barrier()
     d, x, v, t = load_snapshot(w)
     R = args.replicas or w["replicas"]
     K, W = args.steps, args.warmup
