@@ -14,7 +14,7 @@ import time
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("-b", "--box", type=int, default=12)
+    ap.add_argument("-b", "--box", type=int, nargs="+", default=[12], help="box size(s); with several, one table per box: <out>.box<B>")
     ap.add_argument("--promoters", type=int, nargs="+", default=[1, 2, 3])
     ap.add_argument("--activations", type=int, nargs="+", default=[1, 5, 10, 15, 20, 25, 30, 50, 75, 100])
     ap.add_argument("--thresholds", type=int, nargs="+", default=[10, 20, 30, 40, 50, 60, 70, 75, 80, 90, 100])
@@ -30,14 +30,16 @@ def main():
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    t0 = time.time()
-    groups, rows = sweep.run_sweep(args.box, args.promoters, args.activations, args.thresholds, args.repeats, args.total,
-                                   batch_groups=args.batch_groups, device=local,
-                                   progress=lambda r, p, n, left: print(f"rank {r}: promoter {p}: {n} groups done, {left} queued", flush=True))
-    if (dist.get_rank() if dist.is_initialized() else 0) == 0:
-        with open(args.out, "w") as f:
-            f.write(sweep.summary_csv(groups, rows))
-        print(f"{len(groups)} rows -> {args.out} in {time.time() - t0:.1f} s")
+    for box in args.box:
+        t0 = time.time()
+        groups, rows = sweep.run_sweep(box, args.promoters, args.activations, args.thresholds, args.repeats, args.total,
+                                       batch_groups=args.batch_groups, device=local,
+                                       progress=lambda r, p, n, left: print(f"rank {r}: box {box} promoter {p}: {n} groups done, {left} queued", flush=True))
+        if (dist.get_rank() if dist.is_initialized() else 0) == 0:
+            out = args.out if len(args.box) == 1 else f"{args.out}.box{box}"
+            with open(out, "w") as f:
+                f.write(sweep.summary_csv(groups, rows))
+            print(f"box {box}: {len(groups)} rows -> {out} in {time.time() - t0:.1f} s")
     if dist.is_initialized():
         dist.destroy_process_group()
     return 0
