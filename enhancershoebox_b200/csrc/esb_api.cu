@@ -103,6 +103,7 @@ struct esb_handle {
     PairSetup *d_setups = nullptr;
     DevTab *d_tabs_closed = nullptr, *d_tabs_array = nullptr;
     float *d_tabval = nullptr, *d_tabe = nullptr;
+    float4 *d_bref4 = nullptr;
     unsigned int *d_nl_pool = nullptr;
     uint2 *d_nl_qinfo = nullptr;
     esb_chunk_desc *d_descs = nullptr;
@@ -290,7 +291,7 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     k.nry = h->nry; k.nrz = h->nrz; k.nrows = h->nry * h->nrz;
     k.row_inv = (float)(1.0 / h->cell_edge);
     k.qcx = h->qcx; k.qcy = h->qcy; k.qcz = h->qcz; k.qcell_inv = (float)(1.0 / h->quad_edge);
-    k.pos4 = h->d_pos4; k.vel4 = h->d_vel4; k.rs = h->d_rs; k.frozen = h->d_frozen;
+    k.pos4 = h->d_pos4; k.vel4 = h->d_vel4; k.bref4 = h->d_bref4; k.rs = h->d_rs; k.frozen = h->d_frozen;
     k.bterm = h->d_bterm; k.spec = h->d_spec; k.n_topo_pad = h->n_topo_pad;
     k.bterm_stride = h->bterm_stride; k.spec_stride = h->spec_stride;
     if (h->have_actin) { k.act = h->act; k.act_link = h->d_act_link; k.act_lists = h->d_act_lists; k.act_stats = h->d_act_stats; k.act_hist = h->d_act_hist; }
@@ -351,7 +352,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
         rs.seed = 1; rs.r0[1] = 1.0; rs.r0[2] = 0.3; rs.threshold = 80; rs.p_activation_d = 0.03; rs.p_activation = 0.03f;
     }
     const size_t tot = (size_t)n_replicas * h->n_pad;
-    if ((rc = dev_alloc(&h->d_pos4, tot)) || (rc = dev_alloc(&h->d_vel4, tot)) || (rc = dev_alloc(&h->d_rs, (size_t)n_replicas)) ||
+    if ((rc = dev_alloc(&h->d_pos4, tot)) || (rc = dev_alloc(&h->d_vel4, tot)) || (rc = dev_alloc(&h->d_bref4, tot)) || (rc = dev_alloc(&h->d_rs, (size_t)n_replicas)) ||
         (rc = dev_alloc(&h->d_frozen, (size_t)h->n_pad)) || (rc = dev_alloc(&h->d_nl_pool, (size_t)n_replicas * h->n_pad * ESB_NL_STRIDE + 1024)) ||
         (rc = dev_alloc(&h->d_nl_qinfo, 2 * tot)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * ESB_N_COUNTERS)) || (rc = dev_alloc(&h->d_sched, (size_t)n_replicas + 1))) {
         esb_destroy(h);
@@ -380,7 +381,7 @@ int esb_destroy(esb_handle *h)
     cudaFree(h->d_spec); cudaFree(h->d_setups); cudaFree(h->d_tabs_closed); cudaFree(h->d_tabs_array);
     cudaFree(h->d_tabval); cudaFree(h->d_tabe); cudaFree(h->d_nl_pool); cudaFree(h->d_nl_qinfo); cudaFree(h->d_descs);
     cudaFree(h->d_enh); cudaFree(h->d_s5p); cudaFree(h->d_cluster_r); cudaFree(h->d_frames); cudaFree(h->d_rawd); cudaFree(h->d_hist);
-    cudaFree(h->d_counters); cudaFree(h->d_sched);
+    cudaFree(h->d_counters); cudaFree(h->d_sched); cudaFree(h->d_bref4);
     cudaFree(h->d_act_link); cudaFree(h->d_act_lists); cudaFree(h->d_act_stats); cudaFree(h->d_act_hist);
     delete h;
     return ESB_OK;
@@ -880,12 +881,13 @@ int esb_run(esb_handle *h, int chunk_begin, int n_chunks, void *stream)
     KArgs k;
     fill_kargs(h, k, false);
     // a batch that cannot fill the device with two CTAs per SM gets the 32-warp CTA: a replica then advances twice as fast
+    const int n_seg = getenv("ESB_SEG") ? atoi(getenv("ESB_SEG")) : 0;      // 0: the launcher decides
     const bool wide = getenv("ESB_WIDE") ? atoi(getenv("ESB_WIDE")) != 0 : h->R <= h->n_sm;
     if (wide) {
         const size_t smem_w = esb_smem_bytes_v1024(h->n_pad, (int)h->tables.size());
-        CK(esb_launch_run_v1024(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem_w, (cudaStream_t)stream, h->d_sched, h->n_sm));
+        CK(esb_launch_run_v1024(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem_w, (cudaStream_t)stream, h->d_sched, h->n_sm, n_seg));
     } else {
-        CK(esb_launch_run_v512(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem, (cudaStream_t)stream, h->d_sched, h->n_sm));
+        CK(esb_launch_run_v512(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem, (cudaStream_t)stream, h->d_sched, h->n_sm, n_seg));
     }
     return ESB_OK;
 }

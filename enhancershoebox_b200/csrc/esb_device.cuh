@@ -71,7 +71,9 @@ struct ReplicaScalars {       // persistent per-replica state outside the bead a
     double p_activation_d;
     int gene_state, marked, delay, duration, total_active;
     int status;
-    int pad;
+    int ago;                  // steps since the last list build  } carried between the segments of a chunk
+    int rebuild;              // a build is due at the next step  } (a chunk can be run as several work items)
+    int curlist;              // entries of the current lists     }
 };
 
 struct KArgs {
@@ -92,6 +94,7 @@ struct KArgs {
     // device arrays
     float4 *pos4;             // [R][n_pad] x,y,z,type bits
     float4 *vel4;             // [R][n_pad]
+    float4 *bref4;            // [R][n_pad] positions at the last list build, carried between the segments of a chunk
     ReplicaScalars *rs;       // [R]
     const unsigned char *frozen;     // [n_pad]
     uint2 *bterm;             // [ESB_MAX_TERMS][n_topo_pad]  (+ r * bterm_stride: per replica with actin dynamics)
@@ -155,8 +158,8 @@ __device__ __forceinline__ float u32_centered(uint32_t u) { return (float)(int32
 size_t esb_smem_bytes_v512(int n_pad, int n_tables);
 size_t esb_smem_bytes_v1024(int n_pad, int n_tables);
 cudaError_t esb_launch_run_v512(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
-                                int *sched, int n_sm);
+                                int *sched, int n_sm, int n_seg);
 cudaError_t esb_launch_run_v1024(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
-                                 int *sched, int n_sm);
+                                 int *sched, int n_sm, int n_seg);
 cudaError_t esb_launch_forces(const KArgs &k, int pair_mode, int setup_id, float soft_a, int with_post, unsigned long long eval,
                               double *f_out, double *e_out, size_t smem, cudaStream_t st);

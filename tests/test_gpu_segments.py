@@ -1,0 +1,27 @@
+"""A chunk run as several scheduling segments (work items) is the same arithmetic as the chunk in one piece."""
+import numpy as np
+import pytest
+
+from enhancershoebox_b200 import engine as E, protocol as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n_seg", [2, 4, 7])
+def test_segmented_chunks_are_bitwise_identical(box11, snapshots, monkeypatch, n_seg):
+    x, v, t = snapshots["x500"].astype(np.float64), snapshots["v500"].astype(np.float64), snapshots["t500"].astype(np.int32)
+    plans = P.chunk_schedule("genes_stages", n_chunks=503)[500:]
+    out = []
+    for seg in (1, n_seg):
+        monkeypatch.setenv("ESB_SEG", str(seg))
+        eng = E.ShoeboxBatch(box11, n_replicas=5, seeds=[3, 4, 5, 6, 7], thresholds=20, activations=100)
+        eng.upload_state(x[None], v[None], t[None], replicate=True)
+        eng.set_schedule(plans=plans, observe=True)
+        eng.run(0, 2)                                   # two chunks in one launch, then one more
+        eng.run(2, 1)
+        c = eng.counters()
+        out.append(eng.state() + (eng.frames(), eng.status(), c["steps"], c["builds"], c["evals"], c["dangerous"], c["listed"], c["pairs"]))
+        eng.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    assert np.all(out[0][4] == 0) and np.all(out[0][5] == 600)
