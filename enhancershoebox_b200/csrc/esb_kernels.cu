@@ -1395,7 +1395,10 @@ cudaError_t ESB_VARIANT(esb_launch_run)(const KArgs &k, int chunk_begin, int n_c
             const int grid = k.n_replicas < per_sm * n_sm ? k.n_replicas : per_sm * n_sm;   // all CTAs co-resident
             // few chunks over more replicas than CTA slots: cut the chunks into segments so that the last wave is short
             // (measured, 512 replicas on 296 slots: +12 % for 1 chunk, +6 % for 5, -2 % for 10: segments cost ~3 %)
-            if (n_seg <= 0) n_seg = (k.n_replicas > grid && k.n_replicas % grid != 0 && (long long)k.n_replicas * n_chunks < 8LL * grid) ? 4 : 1;
+            if (n_seg <= 0) {
+                const long long items = (long long)k.n_replicas * n_chunks;
+                n_seg = (k.n_replicas <= grid || k.n_replicas % grid == 0 || items >= 8LL * grid) ? 1 : (items < 3LL * grid ? 8 : 4);
+            }
             if (n_seg > 1) {
                 e = cudaFuncSetAttribute(esb_run_kernel<NPC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e == cudaSuccess) esb_run_kernel<NPC, true><<<grid, ESB_THREADS, smem, st>>>(k, chunk_begin, n_chunks, n_seg, delt, sig_nm, sched, sched + 1);
