@@ -156,10 +156,14 @@ def run_reference(args, w):
     d, *_ = load_snapshot(w)
     line = {
         "impl": "reference", "metric": "replica_timesteps_per_s", "value": cb["value"], "unit": "replica-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        # one step of this workload = T_RUN MD steps of every replica of the batch: what that would take at the measured rate
+        "ms_per_step": 1e3 * (args.replicas or w["replicas"]) * T_RUN / cb["value"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "n_atoms": d.n_atoms, "md_steps_per_step": T_RUN, "start_chunk": START_CHUNK,
-                   "note": "CPU restatement of the reference's LAMMPS command stream (LAMMPS itself is not installable here)"},
+                   "replicas_per_gpu": args.replicas or w["replicas"],
+                   "note": "CPU restatement of the reference's LAMMPS command stream (LAMMPS itself is not installable here); "
+                           "ms_per_step = time for one 200-step chunk of the whole batch at the sampled rate"},
         "bead_steps_per_s": cb["bead_steps_per_s"],
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "replica-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
