@@ -87,3 +87,29 @@ def test_pairs_excluded_and_counted(eng, orc, snapshots, box11):
     eng.upload_state(np.stack([x] * 3), np.stack([v] * 3), np.stack([t] * 3))
     fg, _ = eng.forces("B")
     assert np.abs(fg[0] - fo).max() / np.abs(fo).max() < TOL
+
+
+def test_generic_size_path(oracle_lib, pair_tables, oracle_lookup):
+    """A bead count outside the instantiated capacities (box 13: 1516 beads -> n_pad 1536) runs the generic
+    instantiation of the kernels: soft-phase forces at the initial condition and a short run against the oracle."""
+    from enhancershoebox_b200 import datafile, protocol as P
+    d = datafile.make_shoebox(13, 3, False, seed=2)
+    eng = E.ShoeboxBatch(d, n_replicas=2, seeds=[1, 2])
+    assert eng.n_pad not in (1056, 1184, 1312, 1408, 1600)
+    orc = oracle_lib.Oracle(d, pair_tables, oracle_lookup, seed=1)
+    orc.set_pair("soft")
+    orc.L.esbo_pair_soft(orc.h, 30.0, oracle_lib._dp(orc.soft_cut))
+    fo, eo, st = orc.forces()
+    fg, eg = eng.forces("soft", soft_a=30.0)
+    assert st == 0 and np.abs(fg[0] - fo).max() / np.abs(fo).max() < TOL
+    eng.set_schedule(12, observe=True)
+    eng.run(0, 12)                                        # soft phase + the first table chunks
+    assert np.all(eng.status() == 0) and eng.step == 2400
+    x, v, t = eng.state()
+    orc.set_state(t[0], x[0], v[0])
+    orc.L.esbo_set_bond_coeff(orc.h, 1, P.BOND_K, float(eng.bond_r0()[1]))
+    orc.set_pair("A")
+    fo, _, st = orc.forces()
+    fg, _ = eng.forces("A")
+    assert st == 0 and np.abs(fg[0] - fo).max() / np.abs(fo).max() < TOL
+    eng.close()
