@@ -48,3 +48,27 @@ def test_driver_writes_reference_layout_and_aggregates(tmp_path, monkeypatch):
     a2 = dict(a, out=out2, repeats=[3])
     assert drivers.run_condition("genes_stages", a2, n_chunks=n_chunks, quiet=True) == 0
     assert open(os.path.join(out2, "run3", "geneTrack.txt")).read() == open(os.path.join(out, "run3", "geneTrack.txt")).read()
+
+
+def test_failed_repeat_is_rerun_with_a_new_seed(tmp_path, monkeypatch):
+    """The reference launcher deletes the folder of a repeat whose LAMMPS run died and runs it again
+    (run_parallel_shoebox.sh:1-14, 69-75); the batch driver redoes the replicas whose status is non-zero."""
+    monkeypatch.chdir(tmp_path)
+    d = datafile.make_shoebox(9, 3, False, seed=3)
+    calls = []
+
+    class Flaky(E.ShoeboxBatch):
+        def status(self):
+            st = super().status().copy()
+            calls.append(len(st))
+            if len(calls) == 1:
+                st[1] = E.ST_WALL                      # pretend repeat 2 lost an atom in the first attempt
+            return st
+
+    monkeypatch.setattr(drivers, "ShoeboxBatch", Flaky)
+    a = drivers.parse_args("-b 9 -r 1:3 -t 3 -o out/ -m 0 -c Control -p 3 -a 30 -x 80".split(), with_actin=False)
+    assert drivers.run_condition("genes_stages", a, n_chunks=12, data=d, quiet=True) == 0
+    assert calls == [3, 1]                             # second batch: only the failed repeat
+    for r in (1, 2, 3):
+        assert os.path.exists(os.path.join("out", f"run{r}", "figures", "ser5p_cluster.pdf"))
+        assert len(open(os.path.join("out", f"run{r}", "geneTrack.txt")).read().splitlines()) == 12
