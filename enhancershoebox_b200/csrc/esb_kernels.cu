@@ -564,7 +564,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
         const float4 pi = lds128(sb + 16u * (unsigned int)i);
         const int cnt_max = __reduce_max_sync(FULL, cnt);
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-        // The list lives in L2/HBM: four loads per lane are kept in flight (entries e, e+G, e+2G, e+3G)
+        // The list lives in L2/HBM: ESB_PREFETCH loads per lane are kept in flight (entries e, e+G, ...)
         // so that their latency overlaps the arithmetic of the entries before them.
         // Loads past the end of a list are harmless (every bead owns a fixed arena and the pool is padded),
         // so the prefetches carry no predicate; only the use of an entry is guarded.
