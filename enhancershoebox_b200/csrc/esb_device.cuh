@@ -22,8 +22,9 @@
 #define ESB_GROUPS (ESB_THREADS / ESB_G)
 #define ESB_MAX_TERMS 8              // bonded terms per atom (linear chain: 2 bonds + 3 angles)
 #define ESB_MAX_SPEC 8               // excluded partners per atom (linear chain: 6)
-#define ESB_NL_MAXNB 1023            // neighbours per atom (12-bit count in the head word)
-#define ESB_NL_STRIDE 1024           // list arena per bead (entries); LAMMPS: neigh_modify one 10000
+#define ESB_NL_MAXNB 2047            // neighbours per atom in the full list (16-bit count in the descriptor); every
+#define ESB_NL_STRIDE 2048           // bead owns an arena of this many entries: a system of up to 2048 beads cannot
+                                     // overflow it (LAMMPS: neigh_modify one 10000 page 100000, run_single_shoebox.py:533)
 #define ESB_NCLASS 6                 // species classes for the row sort: chromatin-like, actin, RBP, RNP, Ser5P, gene body (induced/active)
 #define ESB_N_COUNTERS 11             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases, dangerous builds
 #define ESB_ACT_WORDS(count) (2 + 3 * (count))
