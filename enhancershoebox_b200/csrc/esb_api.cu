@@ -863,6 +863,9 @@ static int prepare_launch(esb_handle *h, size_t *smem)
         int rc = rebuild_setups(h);
         if (rc) return rc;
     }
+    if ((size_t)12 * h->n_pad < (size_t)(ESB_NL_MAXNB + 1) * 4)
+        return fail(ESB_EINVAL, "replica of %d atoms is too small: the list build keeps %d counters in the force arrays (>= %d beads)",
+                    h->N, ESB_NL_MAXNB + 1, (ESB_NL_MAXNB + 1) / 3 + 1);
     *smem = esb_smem_bytes_v512(h->n_pad, (int)h->tables.size());
     if (*smem > 227 * 1024) return fail(ESB_EINVAL, "replica of %d atoms needs %zu B of shared memory (max 232448)", h->N, *smem);
     return ESB_OK;
