@@ -122,6 +122,9 @@ struct esb_handle {
     int *d_act_stats = nullptr;
     unsigned short *d_act_hist = nullptr;
     size_t bterm_stride = 0, spec_stride = 0;
+    double mic_edges[3][32];
+    int mic_n[3] = {0, 0, 0}, mic_frames = 0;
+    unsigned short *d_mic = nullptr;
     int n_sm = 148;
     Layout lay = {0, 0, 0, 0};
     std::vector<ReplicaScalars> rs_host;
@@ -294,6 +297,11 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     k.pos4 = h->d_pos4; k.vel4 = h->d_vel4; k.bref4 = h->d_bref4; k.rs = h->d_rs; k.frozen = h->d_frozen;
     k.bterm = h->d_bterm; k.spec = h->d_spec; k.n_topo_pad = h->n_topo_pad;
     k.bterm_stride = h->bterm_stride; k.spec_stride = h->spec_stride;
+    if (h->d_mic) {
+        memcpy(k.mic_edges, h->mic_edges, sizeof(k.mic_edges));
+        for (int d = 0; d < 3; d++) k.mic_n[d] = h->mic_n[d];
+        k.mic_frames = h->mic_frames; k.mic_out = h->d_mic;
+    }
     if (h->have_actin) { k.act = h->act; k.act_link = h->d_act_link; k.act_lists = h->d_act_lists; k.act_stats = h->d_act_stats; k.act_hist = h->d_act_hist; }
     k.setups = h->d_setups;
     k.tabs = array_flavour ? h->d_tabs_array : h->d_tabs_closed;
@@ -382,6 +390,7 @@ int esb_destroy(esb_handle *h)
     cudaFree(h->d_tabval); cudaFree(h->d_tabe); cudaFree(h->d_nl_pool); cudaFree(h->d_nl_qinfo); cudaFree(h->d_descs);
     cudaFree(h->d_enh); cudaFree(h->d_s5p); cudaFree(h->d_cluster_r); cudaFree(h->d_frames); cudaFree(h->d_rawd); cudaFree(h->d_hist);
     cudaFree(h->d_counters); cudaFree(h->d_sched); cudaFree(h->d_bref4);
+    cudaFree(h->d_mic);
     cudaFree(h->d_act_link); cudaFree(h->d_act_lists); cudaFree(h->d_act_stats); cudaFree(h->d_act_hist);
     delete h;
     return ESB_OK;
@@ -606,6 +615,39 @@ int esb_get_actin_frames(esb_handle *h, int chunk_begin, int n_chunks, int *stat
                         (size_t)n_chunks * nb * 2, h->R, cudaMemcpyDeviceToHost));
         for (size_t q = 0; q < tmp.size(); q++) hist[q] = tmp[q];
     }
+    return ESB_OK;
+}
+
+int esb_set_microscopy(esb_handle *h, int n_x_edges, const double *x_edges, int n_y_edges, const double *y_edges,
+                       int n_z_edges, const double *z_edges, int n_frames)
+{
+    if (!h || !x_edges || !y_edges || !z_edges || n_frames < 1) return fail(ESB_EINVAL, "bad argument");
+    const int ne[3] = {n_x_edges, n_y_edges, n_z_edges};
+    const double *e[3] = {x_edges, y_edges, z_edges};
+    for (int d = 0; d < 3; d++) {
+        if (ne[d] < 2 || ne[d] > 32) return fail(ESB_EINVAL, "axis %d: %d bin edges (2..32)", d, ne[d]);
+        for (int k = 1; k < ne[d]; k++) if (!(e[d][k] > e[d][k - 1])) return fail(ESB_EINVAL, "axis %d: edges must increase", d);
+    }
+    const size_t nvox = (size_t)(ne[0] - 1) * (ne[1] - 1) * (ne[2] - 1);
+    if (nvox > (size_t)6 * h->n_pad) return fail(ESB_EINVAL, "%zu voxels do not fit the histogram scratch (%d)", nvox, 6 * h->n_pad);
+    CK(cudaSetDevice(h->device));
+    for (int d = 0; d < 3; d++) { h->mic_n[d] = ne[d]; memcpy(h->mic_edges[d], e[d], sizeof(double) * ne[d]); }
+    h->mic_frames = n_frames;
+    int rc;
+    if ((rc = dev_alloc(&h->d_mic, (size_t)h->R * n_frames * 5 * nvox))) return rc;
+    CK(cudaMemset(h->d_mic, 0, (size_t)h->R * n_frames * 5 * nvox * sizeof(unsigned short)));
+    return ESB_OK;
+}
+
+int esb_get_microscopy(esb_handle *h, int frame_begin, int n_frames, unsigned short *out)
+{
+    if (!h || !out) return fail(ESB_EINVAL, "NULL argument");
+    if (!h->d_mic) return fail(ESB_ESTATE, "esb_set_microscopy has not been called");
+    if (frame_begin < 0 || n_frames < 1 || frame_begin + n_frames > h->mic_frames) return fail(ESB_EINVAL, "frame range outside the buffer");
+    CK(cudaSetDevice(h->device));
+    const size_t per = (size_t)5 * (h->mic_n[0] - 1) * (h->mic_n[1] - 1) * (h->mic_n[2] - 1) * sizeof(unsigned short);
+    CK(cudaMemcpy2D(out, (size_t)n_frames * per, h->d_mic + (size_t)frame_begin * per / sizeof(unsigned short), (size_t)h->mic_frames * per,
+                    (size_t)n_frames * per, h->R, cudaMemcpyDeviceToHost));
     return ESB_OK;
 }
 

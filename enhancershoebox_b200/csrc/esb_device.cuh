@@ -102,6 +102,10 @@ struct KArgs {
     unsigned short *spec;     // [n_topo_pad][ESB_MAX_SPEC]   (+ r * spec_stride)
     int n_topo_pad;
     size_t bterm_stride, spec_stride;
+    // synthetic microscopy (mic_out == nullptr: off): bin edges of np.histogramdd per axis, frames kept per replica
+    double mic_edges[3][32];
+    int mic_n[3], mic_frames;
+    unsigned short *mic_out;  // [R][mic_frames][5][nx][ny][nz]
     // actin polymerisation dynamics (act.count == 0: off)
     esb_actin_params act;
     unsigned int *act_link;   // [R][act.count]  neighbour towards the plus end | neighbour towards the minus end << 16 (atom ids, 0xffff none)

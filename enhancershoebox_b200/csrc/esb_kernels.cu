@@ -884,6 +884,50 @@ __device__ __noinline__ void observe(const KArgs &a, int r, const esb_chunk_desc
 
 
 // ------------------------------------------------------------------------------------------------
+// Synthetic microscopy (run_single_shoebox.py:152-213): the voxel counts np.histogramdd would give for the five
+// channels, one channel at a time through a packed-u16 table in the (idle) force arrays.  Bin of a coordinate as in
+// numpy: searchsorted(edges, x, side='right') - 1, a value on the last edge belongs to the last bin, anything outside
+// [first edge, last edge] is dropped; comparisons in fp64 on the fp32 coordinates.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int hist_bin(const double x, const double *edges, const int n_edges)
+{
+    int c = 0;
+    for (int k = 0; k < n_edges; k++) c += (edges[k] <= x);
+    if (x == edges[n_edges - 1]) c -= 1;
+    return (c >= 1 && c <= n_edges - 1) ? c - 1 : -1;
+}
+
+template <int NP>
+__device__ __noinline__ void voxel_counts(const KArgs &a, const int r, const int frame)
+{
+    const Smem S = carve<NP>(a);
+    const int tid = threadIdx.x;
+    const int nx = a.mic_n[0] - 1, ny = a.mic_n[1] - 1, nz = a.mic_n[2] - 1, nvox = nx * ny * nz;
+    unsigned int *cw = reinterpret_cast<unsigned int *>(S.fx);
+    const unsigned int masks[5] = {1u << 8, (1u << 7) | (1u << 11), (1u << 1) | (1u << 2) | (1u << 6) | (1u << 7) | (1u << 9) | (1u << 10) | (1u << 11),
+                                   (1u << 2) | (1u << 6) | (1u << 7) | (1u << 10) | (1u << 11), 1u << 3};
+    unsigned short *out = a.mic_out + ((size_t)r * a.mic_frames + frame) * 5 * (size_t)nvox;
+    for (int ch = 0; ch < 5; ch++) {
+        for (int w = tid; w < (nvox + 1) / 2; w += ESB_THREADS) cw[w] = 0u;
+        __syncthreads();
+        for (int i = tid; i < a.n_atoms; i += ESB_THREADS) {
+            const float4 p = S.pos[i];
+            if (!((masks[ch] >> (__float_as_int(p.w) & 0xff)) & 1u)) continue;
+            const int bx = hist_bin((double)p.x, a.mic_edges[0], a.mic_n[0]);
+            const int by = hist_bin((double)p.y, a.mic_edges[1], a.mic_n[1]);
+            const int bz = hist_bin((double)p.z, a.mic_edges[2], a.mic_n[2]);
+            if ((bx | by | bz) < 0) continue;
+            const int v = (bx * ny + by) * nz + bz;
+            atomicAdd(&cw[v >> 1], 1u << (16 * (v & 1)));
+        }
+        __syncthreads();
+        const unsigned short *c16 = reinterpret_cast<const unsigned short *>(cw);
+        for (int v = tid; v < nvox; v += ESB_THREADS) out[(size_t)ch * nvox + v] = c16[v];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Actin events between two `run` commands (run_single_shoebox.py:969-1298): nucleation of two free
 // monomers, polymerisation at the plus end (every chunk) and at the minus end (every 40th),
 // depolymerisation at the minus end (every 5th), each with the relocation of the moved monomer by
@@ -1248,6 +1292,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         if (SEG) { rs.ago = ago; rs.rebuild = rebuild; rs.curlist = S.misc[M_CURLIST]; }
         if (last_seg && !failed && d.observe) observe<NP>(a, r, d, rs, delt, sig_nm, c);
         if (last_seg && !failed && d.observe && a.act.count > 0) actin_events<NP>(a, r, d, rs, c);
+        if (last_seg && !failed && d.microscopy > 0 && a.mic_out && d.microscopy <= a.mic_frames) voxel_counts<NP>(a, r, d.microscopy - 1);
         ESB_TICK(t_obs)
         __syncthreads();
         failed |= S.misc[M_FAIL];

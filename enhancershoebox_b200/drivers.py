@@ -77,7 +77,8 @@ def parse_args(argv, with_actin: bool):
     return a
 
 
-def run_condition(driver: str, a: dict, n_chunks: int | None = None, device: int = 0, data=None, quiet: bool = False) -> int:
+def run_condition(driver: str, a: dict, n_chunks: int | None = None, device: int = 0, data=None, quiet: bool = False,
+                  make_microscopy: bool = False) -> int:
     """Run the repeats of one condition as a batch and write their folders.  Returns the number of
     repeats that could not be completed."""
     condition = a["condition"]
@@ -105,9 +106,10 @@ def run_condition(driver: str, a: dict, n_chunks: int | None = None, device: int
                 f.write(f"{r},0")
         eng = ShoeboxBatch(data, n_replicas=len(pending), driver=driver, condition=condition, device=device, table_file=table_file,
                            seeds=seeds, thresholds=a["threshold"], activations=a["activation"], p_nucleation=p_nucleation)
-        eng.set_schedule(total, observe=True)
+        eng.set_schedule(total, observe=True, microscopy=make_microscopy)
         eng.run()
         status = eng.status()
+        mic = eng.microscopy() if make_microscopy and eng.mic_chunks else None
         frames, hist = eng.frames(with_hist=True)
         actin = eng.actin_frames() if eng.actin is not None else None
         raw = eng.raw_distances()
@@ -121,6 +123,8 @@ def run_condition(driver: str, a: dict, n_chunks: int | None = None, device: int
             writers.write_run(a["out"], r, frames[k], hist[k], raw[k], int(active[k]), subfolders=subfolders)
             if actin is not None:
                 writers.write_actin(a["out"], r, actin[0][k], actin[1][k])
+            if mic is not None:
+                writers.write_microscopy(a["out"], r, mic[k], eng.mic_chunks)
             if not quiet:
                 print(f"Run {r} done ({int((frames[k][:, 8] == 2).sum())} active frames)")
         attempt += 1
@@ -136,6 +140,6 @@ def main_shoebox(argv=None) -> int:
     return 1 if run_condition("shoebox", a) else 0
 
 
-def main_genes_stages(argv=None) -> int:
+def main_genes_stages(argv=None, make_microscopy: bool = False) -> int:
     a = parse_args(sys.argv[1:] if argv is None else argv, with_actin=False)
-    return 1 if run_condition("genes_stages", a) else 0
+    return 1 if run_condition("genes_stages", a, make_microscopy=make_microscopy) else 0

@@ -40,7 +40,8 @@ class ChunkDesc(C.Structure):
                 ("ramp_on", C.c_int), ("ramp_start", C.c_int64), ("ramp_stop", C.c_int64),
                 ("adapt_soft", C.c_int), ("adapt_bond1", C.c_int), ("adapt_bond2", C.c_int),
                 ("observe", C.c_int), ("expected_rnp", C.c_int),
-                ("induce_on", C.c_int), ("activate_on", C.c_int), ("inactivate_on", C.c_int), ("actin_flags", C.c_int)]
+                ("induce_on", C.c_int), ("activate_on", C.c_int), ("inactivate_on", C.c_int), ("microscopy", C.c_int),
+                ("actin_flags", C.c_int)]
 
 
 class ActinParams(C.Structure):
@@ -69,6 +70,8 @@ _SIGNATURES = {
     "esb_set_fixes": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]),
     "esb_set_neighbor": (C.c_int, [C.c_void_p, C.c_double, C.c_int]),
     "esb_set_actin": (C.c_int, [C.c_void_p, C.POINTER(ActinParams)]),
+    "esb_set_microscopy": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int]),
+    "esb_get_microscopy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_ushort)]),
     "esb_get_actin": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 6),
     "esb_get_actin_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "esb_set_soft": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -299,10 +302,16 @@ class ShoeboxBatch:
     def set_langevin(self, mode: int):
         self._check(self.lib.esb_set_fixes(self.h, P.DT, P.LANGEVIN_T, P.LANGEVIN_DAMP, mode, P.WALL_EPS, P.WALL_CUT))
 
-    def set_schedule(self, n_chunks: int | None = None, observe: bool = True, plans=None, n_steps: int | None = None):
-        """Lay out the drivers' main loop (protocol.chunk_schedule) as the device programme."""
+    def set_schedule(self, n_chunks: int | None = None, observe: bool = True, plans=None, n_steps: int | None = None,
+                     microscopy: bool = False):
+        """Lay out the drivers' main loop (protocol.chunk_schedule) as the device programme.  microscopy: record the
+        synthetic-microscopy voxel counts on every chunk with (i+1) % 10 == 0 (run_single_shoebox.py:1501)."""
         if plans is None:
             plans = P.chunk_schedule(self.driver, self.condition, n_chunks)
+        self.mic_chunks = [pl.index for pl in plans if microscopy and (pl.index + 1) % P.MICROSCOPY_EVERY == 0]
+        if self.mic_chunks:
+            ex, ey, ez = (np.ascontiguousarray(e, np.float64) for e in P.MICROSCOPY_EDGES)
+            self._check(self.lib.esb_set_microscopy(self.h, len(ex), _dp(ex), len(ey), _dp(ey), len(ez), _dp(ez), len(self.mic_chunks)))
         t_rnp_final = 2000 if self.driver == "genes_stages" else P.N_RUNS + P.TREATMENT_DURATION.get(self.condition, 0)
         slope = P.F_RNP_FINAL / (t_rnp_final - P.T_INDUCTION_ON)
         c_rnp = -slope * P.T_INDUCTION_ON
@@ -324,6 +333,7 @@ class ShoeboxBatch:
             d.activate_on = int(P.T_INDUCTION_ON <= i < t_act_off)
             d.inactivate_on = int(i >= P.T_INDUCTION_ON)
             d.actin_flags = P.actin_flags(i, self.condition) if self.actin is not None else 0
+            d.microscopy = 1 + self.mic_chunks.index(i) if i in self.mic_chunks else 0
         self._check(self.lib.esb_set_schedule(self.h, len(plans), descs))
         self.n_chunks = len(plans)
         self.plans = list(plans)
@@ -389,6 +399,14 @@ class ShoeboxBatch:
         hist = np.empty((self.R, n, 49), np.int32)
         self._check(self.lib.esb_get_actin_frames(self.h, chunk_begin, n, _ip(stats), _ip(hist)))
         return stats, hist
+
+    def microscopy(self):
+        """Voxel counts [R, frames, 5, nx, ny, nz] of the chunks in self.mic_chunks; channels Ser5P, Ser2P, chromatin,
+        gene, actin (np.histogramdd of run_single_shoebox.py:157-205)."""
+        shape = tuple(len(e) - 1 for e in P.MICROSCOPY_EDGES)
+        out = np.empty((self.R, len(self.mic_chunks), 5) + shape, np.uint16)
+        self._check(self.lib.esb_get_microscopy(self.h, 0, len(self.mic_chunks), out.ctypes.data_as(C.POINTER(C.c_ushort))))
+        return out
 
     def status(self):
         st = np.empty(self.R, np.int32)

@@ -75,6 +75,13 @@ def actin_flags(i: int, condition: str = "Control") -> int:
     return 1 | (2 if i % (T_ON_PLUS * T_ON_MINUS) == 0 else 0) | (4 if i % T_OFF_MINUS == 0 else 0)
 
 
+# synthetic microscopy (run_single_shoebox.py:152-213, 1498-1502)
+MICROSCOPY_EVERY = 10
+MICROSCOPY_EDGES = (np.linspace(-11, 11, 22), np.linspace(-9, 9, 18), np.linspace(-7, 7, 14))
+MICROSCOPY_CHANNELS = (("Ser5P", (8,)), ("Ser2P", (7, 11)), ("Chromatin", (1, 2, 6, 7, 9, 10, 11)), ("Gene", (2, 6, 7, 10, 11)), ("Actin", (3,)))
+MICROSCOPY_SIGMA = 1
+
+
 TREATMENT_DURATION = {  # run_single_shoebox.py:379-385
     "Hexanediol": int(3 * 60 / 0.6), "JQ-1": int(30 * 60 / 0.6), "Flavopiridol": int(30 * 60 / 0.6),
 }

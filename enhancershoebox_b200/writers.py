@@ -87,6 +87,33 @@ def write_actin(out_folder: str, run_number: int, stats: np.ndarray, hist: np.nd
             f.write(str((i + 1) * P.DELT) + "," + ",".join(str(int(v)) for v in hist[i]) + "\n")
 
 
+def microscopy_stack(counts: np.ndarray, sigma: float = P.MICROSCOPY_SIGMA) -> np.ndarray:
+    """(C, Z, Y, X) float32 image stack of one frame from its voxel counts [5, nx, ny, nz]:
+    gaussian_filter(np.transpose(H, (2, 1, 0)), sigma).astype(np.float32) per channel
+    (run_single_GENE_STAGES_microscopyModif.py:326-353)."""
+    from scipy.ndimage import gaussian_filter
+    return np.stack([gaussian_filter(np.transpose(np.asarray(h, np.float64), (2, 1, 0)), sigma=sigma).astype(np.float32) for h in counts], axis=0)
+
+
+def write_microscopy(out_folder: str, run_number: int, counts: np.ndarray, chunk_indices, t_run: int = P.T_RUN) -> None:
+    """microscopy_files/synthetic_microscopy_<time>.npy (and .ome.tif when tifffile is installed) per recorded chunk:
+    the array the reference hands to tifffile.imwrite / imshow.  time = (i+1)*tRun zero-filled to 7 digits
+    (run_single_shoebox.py:1502).  Rendering PNGs with matplotlib is left to the reference's plotting scripts."""
+    d = os.path.join(out_folder, "run" + str(run_number), "microscopy_files")
+    os.makedirs(d, exist_ok=True)
+    try:
+        import tifffile
+    except Exception:
+        tifffile = None
+    for h, i in zip(counts, chunk_indices):
+        stack = microscopy_stack(h)
+        name = os.path.join(d, "synthetic_microscopy_" + str((i + 1) * t_run).zfill(7))
+        np.save(name + ".npy", stack)
+        if tifffile is not None:
+            tifffile.imwrite(name + ".ome.tif", stack, photometric="minisblack",
+                             metadata={"axes": "CZYX", "Channel": {"Name": [c[0] for c in P.MICROSCOPY_CHANNELS]}})
+
+
 def write_run(out_folder: str, run_number: int, frames: np.ndarray, hist: np.ndarray, raw: np.ndarray, total_active_steps: int,
               n_runs: int = P.N_RUNS, subfolders=("figures", "image_files", "microscopy_files")) -> None:
     """Everything one repeat leaves on disk.  frames [n,9], hist [n,49], raw [n,2] = (d_rp, d_rg) in bead units."""

@@ -73,6 +73,8 @@ typedef struct {
     int induce_on;          /* i >= t_induction_on and i < t_induction_off                    (:1304)      */
     int activate_on;        /* i >= t_activation_on and i < t_activation_off (Flavopiridol: off from NRuns, :885-886, 1322) */
     int inactivate_on;      /* i >= t_activation_on                                           (:1380)      */
+    int microscopy;         /* k > 0: record the synthetic-microscopy voxel counts of this chunk as frame k-1
+                             * ((i+1) % 10 == 0 and make_microscopy, run_single_shoebox.py:1498-1502) */
     int actin_flags;        /* actin events of this chunk (run_single_shoebox.py:969-1298): 1 = nucleation + plus-end
                              * polymerisation ((i+1) >= t_polymerization_on), 2 = minus-end polymerisation
                              * (i % (t_on_plus*t_on_minus) == 0), 4 = minus-end depolymerisation (i % t_off_minus == 0) */
@@ -96,6 +98,14 @@ typedef struct {
     int max_tries;              /* 2000                                                 (:1004)      */
 } esb_actin_params;
 int esb_set_actin(esb_handle *h, const esb_actin_params *p);
+/* makeFakeMicroscopyImages (run_single_shoebox.py:152-213; run_single_GENE_STAGES_microscopyModif.py:301-375): the five
+ * np.histogramdd(positions, bins=(x_edges, y_edges, z_edges)) voxel counts -- Ser5P {8}, Ser2P {7,11}, chromatin
+ * {1,2,6,7,9,10,11}, gene {2,6,7,10,11}, actin {3} -- of every chunk whose descriptor asks for it, fused on the device.
+ * Edges as numpy passes them (np.linspace(-11, 11, 22) ...); n_frames = frames to keep per replica.  The Gaussian blur
+ * and the image files stay on the host.  esb_get_microscopy: out [R][n_frames][5][nx][ny][nz] counts. */
+int esb_set_microscopy(esb_handle *h, int n_x_edges, const double *x_edges, int n_y_edges, const double *y_edges,
+                       int n_z_edges, const double *z_edges, int n_frames);
+int esb_get_microscopy(esb_handle *h, int frame_begin, int n_frames, unsigned short *out);
 /* Filament bookkeeping of every replica after the last run: plus[R][count], minus[R][count] = neighbour of each
  * actin bead towards the plus / minus end (atom id, -1 none); n_free[R], free_list[R][count] = free_actin in list
  * order; n_fil[R], fil_plus[R][count] = plus-end atom of every filament in filament_details order. */

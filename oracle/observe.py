@@ -155,3 +155,15 @@ def frame_record(i: int, meas: dict, state: int, delt: float = 6.0, sig_nm: floa
 def frame_line(rec) -> str:
     """geneTrack.txt line: ``str()`` of each column joined by commas (:1496)."""
     return ",".join(str(v) for v in rec) + "\n"
+
+
+def microscopy_histograms(x: np.ndarray, types: np.ndarray) -> np.ndarray:
+    """The five np.histogramdd voxel counts of makeFakeMicroscopyImages (run_single_shoebox.py:152-205), [5, 21, 17, 13]."""
+    from enhancershoebox_b200 import protocol as P
+    out = []
+    for _name, tset in P.MICROSCOPY_CHANNELS:
+        atoms = np.array([j for j in range(len(types)) if types[j] in tset], dtype=int)
+        positions = np.asarray(x, np.float64)[atoms, :].reshape(-1, 3)
+        H, _ = np.histogramdd(positions, bins=P.MICROSCOPY_EDGES)
+        out.append(H)
+    return np.array(out)
