@@ -283,6 +283,9 @@ def run_native(args, w):
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "traffic": None if not prof else prof.get("dram_bytes_per_step", 0) * K * (R / max(prof.get("replicas", R), 1)),
                          "traffic_source": None if not prof else prof.get("source"),
+                         # from the same committed ncu capture (not measured live): what bounds the kernel in practice
+                         "ncu": None if not prof else {k: prof.get(k) for k in ("ipc", "issue_slot_utilization", "warp_instructions_per_replica_step",
+                                                                                "achieved_occupancy_warps_of_64", "smem_wavefronts_pct_of_peak", "l2_hit_rate_pct")},
                          "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({which} MEASURED_PEAKS.json); MEASURED_PEAKS has no FP32 entry",
                          "kernel": "esb_run_kernel", "launch_ms": ms, "steps_per_launch": K, "flop_per_replica_step": fl,
                          "pairs_in_cut_per_step": pairs_in_cut, "pairs_listed_per_step": listed,
