@@ -1,8 +1,8 @@
 // esb_device.cuh -- device-side data layout and helpers shared by the kernels of libesb.so.
 //
 // One CTA owns one replica: positions (+type), velocities, forces and the positions of the last
-// neighbour build live in shared memory for the whole launch; the neighbour list (full list, u16
-// indices) lives in a per-replica global arena that stays L2-resident.  See DESIGN.md.
+// neighbour build live in shared memory for a whole chunk; the neighbour list (full list, u32 entries =
+// partner index | table id << 16) lives in per-bead arenas of a per-replica global pool.  See DESIGN.md.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -1,8 +1,10 @@
 // esb_kernels.cu -- sm_100a kernels of the EnhancerShoeBox hot path.
 //
-// esb_run_kernel      one CTA per replica; whole replica resident in shared memory; per chunk:
-//                     set-up force evaluation + n_steps x {integrate, (re)build list, forces},
-//                     then the per-chunk measurements / gene state machine / frame record.
+// esb_run_kernel      persistent; one CTA steps one replica at a time (the whole replica is resident in shared
+//                     memory); work items = (replica, chunk[, segment]) from a ticket counter.  Per chunk:
+//                     set-up force evaluation + n_steps x {integrate, (re)build list, forces}, then the per-chunk
+//                     measurements / gene state machine / frame record, the actin events and the synthetic-
+//                     microscopy voxel counts.  This file is compiled twice (ESB_TAG 512 / 1024: CTA size).
 // esb_forces_kernel   parity hook: one force evaluation (+ energies) at the stored positions.
 // esb_pack/unpack     double <-> float4 state conversion for the host-facing ABI.
 //
