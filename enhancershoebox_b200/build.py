@@ -1,7 +1,8 @@
 """Builds libesb.so (CUDA, sm_100a only) in-tree with nvcc.  `python -m enhancershoebox_b200.build`.
 
-esb_kernels.cu is compiled twice (16-warp CTAs x 2 per SM for full batches, 32-warp CTAs x 1 per SM for batches
-smaller than the SM count); the four translation units are compiled in parallel and linked into one library."""
+esb_kernels.cu is compiled three times (16-warp CTAs x 2 per SM for full batches, 32-warp CTAs x 1 per SM for batches
+smaller than the SM count, and the same CTA in thread-block clusters of 2/4/8 per replica for still smaller ones); the
+five translation units are compiled in parallel and linked into one library."""
 from __future__ import annotations
 
 import os
@@ -19,6 +20,7 @@ UNITS = [   # (object, source, extra defines)
     ("esb_api.o", "esb_api.cu", []),
     ("esb_kernels_512.o", "esb_kernels.cu", ["-DESB_TAG=512", "-DESB_THREADS=512", "-DESB_MIN_CTAS=2"]),
     ("esb_kernels_1024.o", "esb_kernels.cu", ["-DESB_TAG=1024", "-DESB_THREADS=1024", "-DESB_MIN_CTAS=1"]),
+    ("esb_kernels_2048.o", "esb_kernels.cu", ["-DESB_TAG=2048", "-DESB_THREADS=1024", "-DESB_MIN_CTAS=1", "-DESB_CLUSTER=1"]),
     ("esb_aggregate.o", "esb_aggregate.cu", []),
 ]
 

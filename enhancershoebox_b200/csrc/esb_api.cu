@@ -928,7 +928,14 @@ int esb_run(esb_handle *h, int chunk_begin, int n_chunks, void *stream)
     // a batch that cannot fill the device with two CTAs per SM gets the 32-warp CTA: a replica then advances twice as fast
     const int n_seg = getenv("ESB_SEG") ? atoi(getenv("ESB_SEG")) : 0;      // 0: the launcher decides
     const bool wide = getenv("ESB_WIDE") ? atoi(getenv("ESB_WIDE")) != 0 : h->R <= h->n_sm;
-    if (wide) {
+    // even smaller batches: a thread-block cluster of 2, 4 or 8 CTAs (SMs) per replica
+    int cluster = 1;
+    if (getenv("ESB_CLUSTER_SIZE")) cluster = atoi(getenv("ESB_CLUSTER_SIZE"));
+    else if (wide) for (int c = 4; c >= 2; c >>= 1) if ((long long)h->R * c <= (long long)h->n_sm * 7 / 8) { cluster = c; break; }   // (8 measured slower than 4)
+    if (cluster == 2 || cluster == 4 || cluster == 8) {
+        const size_t smem_c = esb_smem_bytes_v2048(h->n_pad, (int)h->tables.size());
+        CK(esb_launch_run_v2048(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem_c, (cudaStream_t)stream, h->d_sched, h->n_sm, cluster));
+    } else if (wide) {
         const size_t smem_w = esb_smem_bytes_v1024(h->n_pad, (int)h->tables.size());
         CK(esb_launch_run_v1024(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem_w, (cudaStream_t)stream, h->d_sched, h->n_sm, n_seg));
     } else {

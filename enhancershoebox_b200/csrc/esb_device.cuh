@@ -151,9 +151,11 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // u32 -> uniform in [-0.5, 0.5]; identical to the oracle's u32_to_centered.
 __device__ __forceinline__ float u32_centered(uint32_t u) { return (float)(int32_t)u * 0x1p-32f; }
 
-// esb_kernels.cu is compiled twice into libesb.so: ESB_TAG 512 = 16-warp CTAs, two per SM (full batches), and
+// esb_kernels.cu is compiled three times into libesb.so: ESB_TAG 512 = 16-warp CTAs, two per SM (full batches);
 // ESB_TAG 1024 = 32-warp CTAs, one per SM, which steps a replica twice as fast and is chosen when the batch has
-// no more replicas than the device has SMs (e.g. configs[1]: 64 actin seeds on one GPU).
+// no more replicas than the device has SMs; ESB_TAG 2048 = the same CTA in thread-block clusters of 2/4/8 that step
+// ONE replica together (distributed shared memory), for batches of at most half / a quarter / an eighth of the SMs
+// (e.g. configs[1]: 64 actin seeds on one GPU).
 #ifndef ESB_TAG
 #define ESB_TAG 512
 #endif
@@ -162,6 +164,9 @@ __device__ __forceinline__ float u32_centered(uint32_t u) { return (float)(int32
 #define ESB_VARIANT(name) ESB_CAT2(name##_v, ESB_TAG)
 size_t esb_smem_bytes_v512(int n_pad, int n_tables);
 size_t esb_smem_bytes_v1024(int n_pad, int n_tables);
+size_t esb_smem_bytes_v2048(int n_pad, int n_tables);
+cudaError_t esb_launch_run_v2048(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
+                                 int *sched, int n_sm, int cluster_size);
 cudaError_t esb_launch_run_v512(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
                                 int *sched, int n_sm, int n_seg);
 cudaError_t esb_launch_run_v1024(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,

@@ -16,7 +16,31 @@
 
 #include "esb_device.cuh"
 
+// ESB_CLUSTER = 1 (third compiled variant, ESB_TAG 2048): one replica is stepped by a thread-block CLUSTER of 2, 4 or 8
+// CTAs on as many SMs.  Every CTA keeps the whole replica in its own shared memory; the two expensive loops (candidate
+// scan of the list build, pair loop of the force phase) are split by quad, every bead is integrated by the CTA that
+// owns its quad, and new positions / velocities are written straight into the shared memory of all CTAs of the cluster
+// (distributed shared memory), two cluster barriers per step.  For batches far smaller than the SM count.
+#ifndef ESB_CLUSTER
+#define ESB_CLUSTER 0
+#endif
+#if ESB_CLUSTER
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#endif
+
 namespace {
+
+#if ESB_CLUSTER
+__device__ __forceinline__ int crank() { return (int)cg::this_cluster().block_rank(); }
+__device__ __forceinline__ int csize() { return (int)cg::this_cluster().num_blocks(); }
+__device__ __forceinline__ void csync() { cg::this_cluster().sync(); }
+template <class T>
+__device__ __forceinline__ T *peer(T *p, const int rank) { return cg::this_cluster().map_shared_rank(p, rank); }
+#else
+__device__ __forceinline__ int crank() { return 0; }
+__device__ __forceinline__ int csize() { return 1; }
+#endif
 
 struct Smem {
     float4 *pos;                 // x, y, z, (type | frozen << 8) as int bits
@@ -32,10 +56,16 @@ struct Smem {
     unsigned short *sidx;        // [n_pad]       atom indices sorted by (slot, x); a second [n_pad] block behind it is sort scratch
     float *xs;                   // [n_pad]       x of the sorted beads
     unsigned short *qord;        // [n_pad]       quad order of the build (own region: it outlives the scratch reuse)
+    unsigned char *owner;        // [n_pad]       cluster variant: rank of the CTA that owns the bead (its force quad)
 };
 
 enum { M_QCTR = 0 /* next quad of the running build / force loop */, M_FAIL, M_PAIRS, M_CURLIST, M_SCAN /* one per warp */,
-       M_CNT_PROM = M_SCAN + ESB_THREADS / 32, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */, M_END = M_HIST + 52 };
+       M_CNT_PROM = M_SCAN + ESB_THREADS / 32, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */,
+#if ESB_CLUSTER
+       M_VOTE = M_HIST + 52 /* rebuild vote per rank */, M_CFAIL = M_VOTE + 8 /* failure bits per rank */, M_END = M_CFAIL + 8 };
+#else
+       M_END = M_HIST + 52 };
+#endif
 enum { D_RR = 0, D_PROBE = 3, D_GENE = 6, D_END = 10 };
 
 __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables)
@@ -48,6 +78,9 @@ __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables)
     b += ((size_t)M_END * 4 + 15) & ~(size_t)15;
     b += (size_t)D_END * 8;
     b += (size_t)n_pad * 2;                  // quad order
+#if ESB_CLUSTER
+    b += (size_t)n_pad;                      // bead owners
+#endif
     return (b + 15) & ~(size_t)15;
 }
 
@@ -74,7 +107,8 @@ __device__ __forceinline__ Smem carve(const KArgs &a)
     S.tab = reinterpret_cast<DevTab *>(base + o); o += ((size_t)a.n_tables * sizeof(DevTab) + 15) & ~(size_t)15;
     S.dmisc = reinterpret_cast<double *>(base + o); o += (size_t)D_END * 8;
     S.misc = reinterpret_cast<int *>(base + o); o += ((size_t)M_END * 4 + 15) & ~(size_t)15;
-    S.qord = reinterpret_cast<unsigned short *>(base + o);
+    S.qord = reinterpret_cast<unsigned short *>(base + o); o += (size_t)np * 2;
+    S.owner = reinterpret_cast<unsigned char *>(base + o);
     S.cend = reinterpret_cast<unsigned short *>(S.fx);
     S.sidx = S.cend + ((a.nrows * ESB_NCLASS + 2 + 7) & ~7);
     S.xs = reinterpret_cast<float *>(S.sidx + 2 * np);
@@ -257,7 +291,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         // quads are handed out dynamically: their cost varies by two orders of magnitude with the species
         int q = 0;
         if (lane == 0) q = atomicAdd(&S.misc[M_QCTR], 1);
-        q = __shfl_sync(FULL, q, 0);
+        q = __shfl_sync(FULL, q, 0) * csize() + crank();         // (cluster variant: the quads are dealt to the CTAs of the cluster)
         if (q >= nquads) break;
         int ia[4], ta[4], cnt[4];
         float4 pa[4];
@@ -413,13 +447,17 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
     }
     if (listed) atomicAdd(&S.misc[M_CURLIST], (int)listed);
     __syncthreads();
+#if ESB_CLUSTER
+    __threadfence();
+    csync();                                                     // the descriptors of all quads (global) are written
+#endif
     // ---- force order: descriptors sorted by decreasing list length (counting sort on the length) ----
-    {
+    if (crank() == 0) {
         uint2 *qforce = a.nl_qinfo + (size_t)r * 2 * a.n_pad;
         int *hist = reinterpret_cast<int *>(S.fx);                 // 1024 counters; the scratch is free again
         for (int k = tid; k < ESB_NL_MAXNB + 1; k += ESB_THREADS) hist[k] = 0;
         __syncthreads();
-        for (int k = tid; k < n; k += ESB_THREADS) atomicAdd(&hist[ESB_NL_MAXNB - (int)(qbuild[k].y >> 16)], 1);
+        for (int k = tid; k < n; k += ESB_THREADS) atomicAdd(&hist[ESB_NL_MAXNB - (int)(__ldcg(&qbuild[k]).y >> 16)], 1);
         __syncthreads();
         // exclusive scan of the 1024 counters: an equal share per thread
         constexpr int PER = (ESB_NL_MAXNB + ESB_THREADS) / ESB_THREADS;
@@ -440,11 +478,20 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         for (int k = 0; k < PER; k++) { if (PER * tid + k <= ESB_NL_MAXNB) hist[PER * tid + k] = base; base += v[k]; }
         __syncthreads();
         for (int k = tid; k < n; k += ESB_THREADS) {
-            const uint2 d = qbuild[k];
-            qforce[atomicAdd(&hist[ESB_NL_MAXNB - (int)(d.y >> 16)], 1)] = d;
+            const uint2 d = __ldcg(&qbuild[k]);
+            const int at = atomicAdd(&hist[ESB_NL_MAXNB - (int)(d.y >> 16)], 1);
+            qforce[at] = d;
+#if ESB_CLUSTER
+            // the CTA that takes force quad at/4 owns the bead: bonded terms, pair loop, integration
+            for (int rk = 0; rk < csize(); rk++) peer(S.owner, rk)[d.y & 0xffffu] = (unsigned char)((at >> 2) % csize());
+#endif
         }
     }
     __syncthreads();   // lists (global) and the scratch alias are settled before forces are written
+#if ESB_CLUSTER
+    __threadfence();
+    csync();                                                     // force order (global) and owners (every CTA) are in place
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -461,6 +508,9 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
     const int n = a.n_atoms, n_topo = a.n_topo, ntp = a.n_topo_pad;
     const uint2 *bterm = a.bterm + (size_t)r * a.bterm_stride;     // per replica when the actin topology is dynamic
     for (int i = threadIdx.x; i < n; i += ESB_THREADS) {
+#if ESB_CLUSTER
+        if (S.owner[i] != crank()) continue;                     // another CTA of the cluster owns this bead
+#endif
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
         if (i < n_topo) {
             const float4 pi = S.pos[i];
@@ -550,7 +600,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
     auto next_quad = [&]() {
         int t = 0;
         if (lane == 0) t = atomicAdd(&S.misc[M_QCTR], 1);
-        return __shfl_sync(FULL, t, 0);
+        return __shfl_sync(FULL, t, 0) * csize() + crank();
     };
     int q = next_quad();
     uint2 qi = make_uint2(0u, 0u);
@@ -711,6 +761,9 @@ __device__ __noinline__ int atom_phase(const KArgs &a, const bool do_final, cons
     const float dtf = 0.5f * a.dt, dtv = a.dt;
     double dummy = 0.0;
     for (int i = threadIdx.x; i < a.n_atoms; i += ESB_THREADS) {
+#if ESB_CLUSTER
+        if (S.owner[i] != crank()) continue;                     // integrated by its owner, which writes it into every CTA
+#endif
         float4 p = S.pos[i];
         float vx = S.vx[i], vy = S.vy[i], vz = S.vz[i];
         float fx = S.fx[i], fy = S.fy[i], fz = S.fz[i];
@@ -720,11 +773,20 @@ __device__ __noinline__ int atom_phase(const KArgs &a, const bool do_final, cons
         if (do_initial) {
             vx += dtf * fx; vy += dtf * fy; vz += dtf * fz;
             p.x += dtv * vx; p.y += dtv * vy; p.z += dtv * vz;
+#if !ESB_CLUSTER
             S.pos[i] = p;
+#endif
             const float ex = p.x - S.bx[i], ey = p.y - S.by[i], ez = p.z - S.bz[i];
             if (ex * ex + ey * ey + ez * ez > a.skin_half_sq) flags |= 1;
         }
+#if ESB_CLUSTER
+        for (int rk = 0; rk < csize(); rk++) {                   // distributed shared memory: the same arrays of every CTA
+            if (do_initial) peer(S.pos, rk)[i] = p;
+            peer(S.vx, rk)[i] = vx; peer(S.vy, rk)[i] = vy; peer(S.vz, rk)[i] = vz;
+        }
+#else
         S.vx[i] = vx; S.vy[i] = vy; S.vz[i] = vz;
+#endif
     }
     return flags;
 }
@@ -1195,20 +1257,36 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
     // grain: a launch of few chunks over more replicas than CTA slots then packs the SMs better).
     const int n_items = a.n_replicas * n_chunks * n_seg;
 
+    const int crk = crank();
     for (;;) {
         __syncthreads();
+#if ESB_CLUSTER
+        csync();                                                     // nobody of the cluster still reads the previous item
+        if (crk == 0 && tid == 0) {                                  // the cluster takes ONE item: rank 0 draws it and waits for its turn
+            const int it_ = atomicAdd(ticket, 1);
+            if (it_ < n_items) {
+                while (atomicAdd(&progress[it_ % a.n_replicas], 0) < it_ / a.n_replicas) __nanosleep(256);
+                __threadfence();
+            }
+            for (int rk = 0; rk < csize(); rk++) *peer(&s_item, rk) = it_;
+        }
+        csync();
+#else
         if (tid == 0) s_item = atomicAdd(ticket, 1);
         __syncthreads();
+#endif
         const int item = s_item;
         if (item >= n_items) break;
         const int r = item % a.n_replicas, seq = item / a.n_replicas;      // seq = (local chunk, segment) of this replica, in order
         const int lc = SEG ? seq / n_seg : seq, seg = SEG ? seq - lc * n_seg : 0;
         const int c = chunk_begin + lc;
+#if !ESB_CLUSTER
         if (tid == 0) {
             while (atomicAdd(&progress[r], 0) < seq) __nanosleep(256);
             __threadfence();
         }
         __syncthreads();
+#endif
         ReplicaScalars rs;
         {
             const volatile int *src = reinterpret_cast<const volatile int *>(&a.rs[r]);
@@ -1220,7 +1298,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         const int it0 = SEG ? seg * seg_len : 0, it1 = SEG ? min(it0 + seg_len, n_steps_c + 1) : n_steps_c + 1;
         if (rs.status != 0 || (SEG && it0 >= it1)) {                         // a failed replica no longer advances
             __syncthreads();
-            if (tid == 0) { __threadfence(); atomicExch(&progress[r], seq + 1); }
+            if (tid == 0 && crk == 0) { __threadfence(); atomicExch(&progress[r], seq + 1); }
             continue;
         }
         for (int k = tid; k < np; k += ESB_THREADS) {
@@ -1275,7 +1353,18 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             // post_force of this evaluation, final integrate of the step it closes (it > 0) and initial
             // integrate of the next one (it < n_steps).  __syncthreads_or only tells whether ANY thread
             // passed non-zero, so it carries the rebuild vote; failure bits travel through shared memory.
+#if ESB_CLUSTER
+            csync();                                                 // every CTA of the cluster is done reading the old positions
+#endif
             rebuild = __syncthreads_or(atom_phase<NP>(a, it > 0, it < d.n_steps, k0, k1, rs.eval));
+#if ESB_CLUSTER
+            if (tid == 0)
+                for (int rk = 0; rk < csize(); rk++) { peer(S.misc, rk)[M_VOTE + crk] = rebuild; peer(S.misc, rk)[M_CFAIL + crk] = S.misc[M_FAIL]; }
+            csync();                                                 // new positions, votes and failure bits of all CTAs have landed
+            rebuild = 0;
+            for (int rk = 0; rk < csize(); rk++) { rebuild |= S.misc[M_VOTE + rk]; if (S.misc[M_CFAIL + rk]) S.misc[M_FAIL] = S.misc[M_FAIL] | S.misc[M_CFAIL + rk]; }
+            __syncthreads();
+#endif
             ago++;
             rebuild = rebuild && (ago >= delay);
             rs.eval++;
@@ -1292,12 +1381,21 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         }
         const unsigned long long n_pairs = (unsigned int)S.misc[M_PAIRS];
         if (SEG) { rs.ago = ago; rs.rebuild = rebuild; rs.curlist = S.misc[M_CURLIST]; }
+        if (crk == 0) {                                                      // (cluster variant: every CTA holds the same state; one of them reports)
         if (last_seg && !failed && d.observe) observe<NP>(a, r, d, rs, delt, sig_nm, c);
         if (last_seg && !failed && d.observe && a.act.count > 0) actin_events<NP>(a, r, d, rs, c);
         if (last_seg && !failed && d.microscopy > 0 && a.mic_out && d.microscopy <= a.mic_frames) voxel_counts<NP>(a, r, d.microscopy - 1);
+        }
         ESB_TICK(t_obs)
         __syncthreads();
         failed |= S.misc[M_FAIL];
+#if ESB_CLUSTER
+        if (tid == 0) {                                                       // pair statistics: every CTA saw its own quads
+            unsigned long long *cn = a.counters + (size_t)r * ESB_N_COUNTERS;
+            atomicAdd(&cn[2], n_pairs); atomicAdd(&cn[3], n_listed);
+        }
+        if (crk != 0) continue;
+#endif
         for (int k = tid; k < np; k += ESB_THREADS) {
             a.pos4[(size_t)r * np + k] = S.pos[k];
             a.vel4[(size_t)r * np + k] = make_float4(S.vx[k], S.vy[k], S.vz[k], 0.0f);
@@ -1310,8 +1408,10 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             cn[6] += (unsigned long long)t_atom; cn[7] += (unsigned long long)t_build;
             cn[8] += (unsigned long long)t_force; cn[9] += (unsigned long long)t_obs;
             cn[0] += n_evals; cn[1] += n_builds;
+#if !ESB_CLUSTER
             cn[2] += n_pairs;
             cn[3] += n_listed;
+#endif
             cn[4] += n_steps_done;
             cn[5] = (unsigned long long)rs.total_active;
             cn[10] += n_danger;
@@ -1428,6 +1528,34 @@ size_t ESB_VARIANT(esb_smem_bytes)(int n_pad, int n_tables) { return smem_bytes_
         default: { constexpr int NPC = 0; __VA_ARGS__; break; }      \
     }
 
+#if ESB_CLUSTER
+// Cluster variant: n_seg carries the cluster size (2, 4 or 8 CTAs per replica); one cluster per co-resident replica.
+cudaError_t ESB_VARIANT(esb_launch_run)(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
+                                        int *sched /* [1 + n_replicas] device ints: ticket, progress[] */, int n_sm, int cluster_size)
+{
+    (void)n_sm;
+    cudaError_t e = cudaSuccess;
+    ESB_FOR_NP(k.n_pad, {
+        auto kern = esb_run_kernel<NPC, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned int)cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned int)(cluster_size * k.n_replicas)); cfg.blockDim = dim3(ESB_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg);
+        if (e == cudaSuccess && n_clusters < 1) e = cudaErrorLaunchOutOfResources;
+        if (e == cudaSuccess) e = cudaMemsetAsync(sched, 0, sizeof(int) * (size_t)(1 + k.n_replicas), st);
+        if (e == cudaSuccess) {
+            cfg.gridDim = dim3((unsigned int)(cluster_size * (k.n_replicas < n_clusters ? k.n_replicas : n_clusters)));   // all clusters co-resident
+            e = cudaLaunchKernelEx(&cfg, kern, k, chunk_begin, n_chunks, 1, delt, sig_nm, sched, sched + 1);
+        }
+    })
+    return e;
+}
+#else
 cudaError_t ESB_VARIANT(esb_launch_run)(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
                                         int *sched /* [1 + n_replicas] device ints: ticket, progress[] */, int n_sm, int n_seg)
 {
@@ -1457,6 +1585,8 @@ cudaError_t ESB_VARIANT(esb_launch_run)(const KArgs &k, int chunk_begin, int n_c
     })
     return e;
 }
+
+#endif   // !ESB_CLUSTER
 
 #if ESB_TAG == 512
 cudaError_t esb_launch_forces(const KArgs &k, int pair_mode, int setup_id, float soft_a, int with_post, unsigned long long eval,

@@ -25,3 +25,25 @@ def test_segmented_chunks_are_bitwise_identical(box11, snapshots, monkeypatch, n
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a, b)
     assert np.all(out[0][4] == 0) and np.all(out[0][5] == 600)
+
+
+@pytest.mark.parametrize("cluster", [2, 4, 8])
+def test_cluster_of_ctas_per_replica_is_bitwise_identical(box11, snapshots, monkeypatch, cluster):
+    """Small batches are stepped by a thread-block cluster per replica (quads split over the CTAs, positions exchanged
+    through distributed shared memory): every bead sees the same arithmetic as in the one-CTA kernel."""
+    x, v, t = snapshots["x500"].astype(np.float64), snapshots["v500"].astype(np.float64), snapshots["t500"].astype(np.int32)
+    plans = P.chunk_schedule("genes_stages", n_chunks=503)[500:]
+    out = []
+    for size in (1, cluster):
+        monkeypatch.setenv("ESB_CLUSTER_SIZE", str(size))
+        eng = E.ShoeboxBatch(box11, n_replicas=3, seeds=[3, 4, 5], thresholds=20, activations=100)
+        eng.upload_state(x[None], v[None], t[None], replicate=True)
+        eng.set_schedule(plans=plans, observe=True)
+        eng.run(0, 2)
+        eng.run(2, 1)
+        c = eng.counters()
+        out.append(eng.state() + (eng.frames(), eng.status(), c["steps"], c["builds"], c["evals"], c["dangerous"], c["listed"], c["pairs"]))
+        eng.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    assert np.all(out[0][4] == 0) and np.all(out[0][5] == 600)
