@@ -45,7 +45,8 @@ __device__ __forceinline__ int csize() { return 1; }
 struct Smem {
     float4 *pos;                 // x, y, z, (type | frozen << 8) as int bits
     float *vx, *vy, *vz;
-    float *fx, *fy, *fz;         // forces; the same bytes serve as scratch during a list build
+    float *fx, *fy, *fz;         // pair forces; the same bytes serve as scratch during a list build
+    float *gx, *gy, *gz;         // bonded forces (own arrays: the bonded pass and the pair loop run without a barrier between them)
     float *bx, *by, *bz;         // positions at the last neighbour build
     PairSetup *setup;
     DevTab *tab;
@@ -57,12 +58,15 @@ struct Smem {
     float *xs;                   // [n_pad]       x of the sorted beads
     unsigned short *qord;        // [n_pad]       quad order of the build (own region: it outlives the scratch reuse)
     unsigned char *owner;        // [n_pad]       cluster variant: rank of the CTA that owns the bead (its force quad)
+    float4 *pos_next;            // cluster variant: the other position buffer (written by the per-atom phase of all CTAs)
+    unsigned short *mine;        // cluster variant: the beads this CTA owns (any order), misc[M_NMINE] of them
 };
 
 enum { M_QCTR = 0 /* next quad of the running build / force loop */, M_FAIL, M_PAIRS, M_CURLIST, M_SCAN /* one per warp */,
        M_CNT_PROM = M_SCAN + ESB_THREADS / 32, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */,
 #if ESB_CLUSTER
-       M_VOTE = M_HIST + 52 /* rebuild vote per rank */, M_CFAIL = M_VOTE + 8 /* failure bits per rank */, M_END = M_CFAIL + 8 };
+       M_PARITY = M_HIST + 52 /* which of the two position buffers is current */, M_NMINE /* beads this CTA owns */, M_VOTE /* rebuild vote [parity][rank] */,
+       M_CFAIL = M_VOTE + 16 /* failure bits [parity][rank] */, M_END = M_CFAIL + 16 };
 #else
        M_END = M_HIST + 52 };
 #endif
@@ -72,14 +76,16 @@ __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables)
 {
     size_t b = 0;
     b += (size_t)n_pad * 16;                 // pos
-    b += (size_t)n_pad * 4 * 9;              // v, f, xbuild
+    b += (size_t)n_pad * 4 * 12;             // v, f (pair), f (bonded), xbuild
     b += (sizeof(PairSetup) + 15) & ~(size_t)15;
     b += ((size_t)n_tables * sizeof(DevTab) + 15) & ~(size_t)15;
     b += ((size_t)M_END * 4 + 15) & ~(size_t)15;
     b += (size_t)D_END * 8;
     b += (size_t)n_pad * 2;                  // quad order
 #if ESB_CLUSTER
-    b += (size_t)n_pad;                      // bead owners
+    b += ((size_t)n_pad + 15) & ~(size_t)15; // bead owners
+    b += (size_t)n_pad * 16;                 // second position buffer (the CTAs of a cluster write the next positions there)
+    b += (size_t)n_pad * 2;                  // the beads this CTA owns
 #endif
     return (b + 15) & ~(size_t)15;
 }
@@ -87,7 +93,7 @@ __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables)
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
 template <int NP>
-__device__ __forceinline__ Smem carve(const KArgs &a)
+__device__ __forceinline__ Smem carve(const KArgs &a, const bool first_buffer = false)
 {
     const int np = NP ? NP : a.n_pad;   // compile-time bead capacity: every array offset is an immediate
     Smem S;
@@ -100,6 +106,9 @@ __device__ __forceinline__ Smem carve(const KArgs &a)
     S.fx = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.fy = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.fz = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.gx = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.gy = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
+    S.gz = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.bx = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.by = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.bz = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
@@ -109,6 +118,15 @@ __device__ __forceinline__ Smem carve(const KArgs &a)
     S.misc = reinterpret_cast<int *>(base + o); o += ((size_t)M_END * 4 + 15) & ~(size_t)15;
     S.qord = reinterpret_cast<unsigned short *>(base + o); o += (size_t)np * 2;
     S.owner = reinterpret_cast<unsigned char *>(base + o);
+#if ESB_CLUSTER
+    o += ((size_t)np + 15) & ~(size_t)15;
+    {   // double-buffered positions: the current buffer is selected by a flag that only changes between phases
+        float4 *alt = reinterpret_cast<float4 *>(base + o);
+        S.pos_next = alt;
+        if (!first_buffer && S.misc[M_PARITY]) { S.pos_next = S.pos; S.pos = alt; }
+        S.mine = reinterpret_cast<unsigned short *>(base + o + (size_t)np * 16);
+    }
+#endif
     S.cend = reinterpret_cast<unsigned short *>(S.fx);
     S.sidx = S.cend + ((a.nrows * ESB_NCLASS + 2 + 7) & ~7);
     S.xs = reinterpret_cast<float *>(S.sidx + 2 * np);
@@ -144,7 +162,7 @@ template <int NP>
 __device__ __forceinline__ int tab_off4(const KArgs &a)
 {
     const int np = NP ? NP : a.n_pad;
-    return (np * 52 + (int)((sizeof(PairSetup) + 15) & ~(size_t)15)) / 16;   // float4 index of S.tab
+    return (np * 64 + (int)((sizeof(PairSetup) + 15) & ~(size_t)15)) / 16;   // float4 index of S.tab
 }
 
 __device__ __forceinline__ int cell_coord(float x, float lo, float inv, int n)
@@ -487,10 +505,24 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
 #endif
         }
     }
+#if ESB_CLUSTER
+    if (tid == 0) S.misc[M_NMINE] = 0;
+#endif
+    if (tid == 0) S.misc[M_QCTR] = 0;                            // the force loop hands out quads from 0
     __syncthreads();   // lists (global) and the scratch alias are settled before forces are written
 #if ESB_CLUSTER
     __threadfence();
     csync();                                                     // force order (global) and owners (every CTA) are in place
+    for (int i0 = warp * 32; i0 < n; i0 += ESB_THREADS) {        // dense list of the owned beads: full warps in the per-bead loops
+        const int i = i0 + lane;
+        const bool own = i < n && S.owner[i] == crank();
+        const unsigned int m = __ballot_sync(FULL, own);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&S.misc[M_NMINE], __popc(m));
+        base = __shfl_sync(FULL, base, 0);
+        if (own) S.mine[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
+    }
+    __syncthreads();
 #endif
 }
 
@@ -507,9 +539,11 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
 {
     const int n = a.n_atoms, n_topo = a.n_topo, ntp = a.n_topo_pad;
     const uint2 *bterm = a.bterm + (size_t)r * a.bterm_stride;     // per replica when the actin topology is dynamic
-    for (int i = threadIdx.x; i < n; i += ESB_THREADS) {
 #if ESB_CLUSTER
-        if (S.owner[i] != crank()) continue;                     // another CTA of the cluster owns this bead
+    for (int k = threadIdx.x; k < S.misc[M_NMINE]; k += ESB_THREADS) {   // the other beads belong to other CTAs of the cluster
+        const int i = S.mine[k];
+#else
+    for (int i = threadIdx.x; i < n; i += ESB_THREADS) {
 #endif
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
         if (i < n_topo) {
@@ -559,7 +593,7 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
                 }
             }
         }
-        S.fx[i] = fx; S.fy[i] = fy; S.fz[i] = fz;
+        S.gx[i] = fx; S.gy[i] = fy; S.gz[i] = fz;
     }
 }
 
@@ -585,12 +619,17 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
     const int lane = tid & 31;
     const int gl = lane & (ESB_G - 1), grp = lane / ESB_G;
     double e_pair = 0.0, e_bond = 0.0, e_angle = 0.0;
+    // no barrier between the two: the bonded pass writes S.g*, the pair loop S.f*; a warp whose beads have no
+    // bonded terms starts on the quads while the others wait for their term rows.  (S.misc[M_QCTR] is 0 on entry.)
     bonded_forces<ENERGY>(S, a, r, r0_1, r0_2, e_bond, e_angle);
-    if (tid == 0) S.misc[M_QCTR] = 0;
-    __syncthreads();
     const unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESB_NL_STRIDE;
     const uint2 *qinfo = a.nl_qinfo + (size_t)r * 2 * a.n_pad;
+#if ESB_CLUSTER
+    const unsigned int sb0 = smem_base(), tbase = sb0 + 16u * (unsigned int)tab_off4<NP>(a);
+    const unsigned int sb = sb0 + (unsigned int)(reinterpret_cast<unsigned char *>(S.pos) - smem_raw);      // current position buffer
+#else
     const unsigned int sb = smem_base(), tbase = sb + 16u * (unsigned int)tab_off4<NP>(a);
+#endif
     const float *tabval = a.tabval;
     const int tlm1 = a.tlm1;
     unsigned int npairs = 0;
@@ -693,7 +732,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
             fy += __shfl_xor_sync(FULL, fy, d);
             fz += __shfl_xor_sync(FULL, fz, d);
         }
-        if (valid && gl == 0) { S.fx[i] += fx; S.fy[i] += fy; S.fz[i] += fz; }
+        if (valid && gl == 0) { S.fx[i] = fx; S.fy[i] = fy; S.fz[i] = fz; }
         q = qn; qi = qi_next;
     }
     if (npairs) atomicAdd(&S.misc[M_PAIRS], (int)npairs);
@@ -760,13 +799,15 @@ __device__ __noinline__ int atom_phase(const KArgs &a, const bool do_final, cons
     int flags = 0;
     const float dtf = 0.5f * a.dt, dtv = a.dt;
     double dummy = 0.0;
-    for (int i = threadIdx.x; i < a.n_atoms; i += ESB_THREADS) {
 #if ESB_CLUSTER
-        if (S.owner[i] != crank()) continue;                     // integrated by its owner, which writes it into every CTA
+    for (int k = threadIdx.x; k < S.misc[M_NMINE]; k += ESB_THREADS) {   // integrated by its owner, which writes it into every CTA
+        const int i = S.mine[k];
+#else
+    for (int i = threadIdx.x; i < a.n_atoms; i += ESB_THREADS) {
 #endif
         float4 p = S.pos[i];
         float vx = S.vx[i], vy = S.vy[i], vz = S.vz[i];
-        float fx = S.fx[i], fy = S.fy[i], fz = S.fz[i];
+        float fx = S.gx[i] + S.fx[i], fy = S.gy[i] + S.fy[i], fz = S.gz[i] + S.fz[i];    // bonded + pair
         const int fail = post_force<false>(a, i, p, vx, vy, vz, fx, fy, fz, k0, k1, eval, dummy);
         if (fail) atomicOr(&S.misc[M_FAIL], fail);
         if (do_final) { vx += dtf * fx; vy += dtf * fy; vz += dtf * fz; }
@@ -780,16 +821,29 @@ __device__ __noinline__ int atom_phase(const KArgs &a, const bool do_final, cons
             if (ex * ex + ey * ey + ez * ez > a.skin_half_sq) flags |= 1;
         }
 #if ESB_CLUSTER
-        for (int rk = 0; rk < csize(); rk++) {                   // distributed shared memory: the same arrays of every CTA
-            if (do_initial) peer(S.pos, rk)[i] = p;
-            peer(S.vx, rk)[i] = vx; peer(S.vy, rk)[i] = vy; peer(S.vz, rk)[i] = vz;
-        }
-#else
-        S.vx[i] = vx; S.vy[i] = vy; S.vz[i] = vz;
+        if (do_initial)                                          // distributed shared memory: the other position buffer of every CTA
+            for (int rk = 0; rk < csize(); rk++) peer(S.pos_next, rk)[i] = p;    // (nobody reads it during this step)
 #endif
+        S.vx[i] = vx; S.vy[i] = vy; S.vz[i] = vz;                // (cluster: only the owner needs the velocity until ownership changes)
     }
     return flags;
 }
+
+#if ESB_CLUSTER
+// Velocities live with the bead's owner; they are handed to every CTA of the cluster before the ownership changes
+// (a list build re-deals the beads) and before the state is stored.  The next cluster barrier publishes them.
+template <int NP>
+__device__ __noinline__ void publish_velocities(const KArgs &a)
+{
+    const Smem S = carve<NP>(a);
+    for (int k = threadIdx.x; k < S.misc[M_NMINE]; k += ESB_THREADS) {
+        const int i = S.mine[k];
+        const float vx = S.vx[i], vy = S.vy[i], vz = S.vz[i];
+        for (int rk = 0; rk < csize(); rk++)
+            if (rk != crank()) { peer(S.vx, rk)[i] = vx; peer(S.vy, rk)[i] = vy; peer(S.vz, rk)[i] = vz; }
+    }
+}
+#endif
 
 // [LAMMPS-ext] Variable ramp(x,y): delta = step - start; if (delta != 0) delta /= stop - start; x + delta*(y-x),
 // evaluated by fix adapt at set-up and every nevery steps (run_single_shoebox.py:627-639); `run 0` gives x.
@@ -1247,7 +1301,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
                int *ticket, int *progress)
 {
     const int n_seg = SEG ? n_seg_arg : 1;          // SEG = false: the plain one-item-per-chunk kernel, compiled without the segment code
-    const Smem S = carve<NP>(a);
+    const Smem S = carve<NP>(a, true);
     const int tid = threadIdx.x;
     const int np = NP ? NP : a.n_pad;
     for (int k = tid; k < a.n_tables * (int)(sizeof(DevTab) / 4); k += ESB_THREADS)
@@ -1348,25 +1402,33 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             else force_phase<NP, 2, false>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
             n_evals++;
             __syncthreads();
+            if (tid == 0) S.misc[M_QCTR] = 0;                        // (visible to the next force loop through the per-atom phase's barrier)
             ESB_TICK(t_force)
             n_listed += (unsigned int)S.misc[M_CURLIST];
             // post_force of this evaluation, final integrate of the step it closes (it > 0) and initial
             // integrate of the next one (it < n_steps).  __syncthreads_or only tells whether ANY thread
             // passed non-zero, so it carries the rebuild vote; failure bits travel through shared memory.
-#if ESB_CLUSTER
-            csync();                                                 // every CTA of the cluster is done reading the old positions
-#endif
             rebuild = __syncthreads_or(atom_phase<NP>(a, it > 0, it < d.n_steps, k0, k1, rs.eval));
 #if ESB_CLUSTER
-            if (tid == 0)
-                for (int rk = 0; rk < csize(); rk++) { peer(S.misc, rk)[M_VOTE + crk] = rebuild; peer(S.misc, rk)[M_CFAIL + crk] = S.misc[M_FAIL]; }
-            csync();                                                 // new positions, votes and failure bits of all CTAs have landed
-            rebuild = 0;
-            for (int rk = 0; rk < csize(); rk++) { rebuild |= S.misc[M_VOTE + rk]; if (S.misc[M_CFAIL + rk]) S.misc[M_FAIL] = S.misc[M_FAIL] | S.misc[M_CFAIL + rk]; }
-            __syncthreads();
+            {   // ONE cluster barrier per step: the next positions went into the other buffer of every CTA, votes and
+                // failure bits into slots of this step's parity (a CTA is never more than one barrier ahead)
+                const int par = it & 1;
+                if (tid == 0)
+                    for (int rk = 0; rk < csize(); rk++) { peer(S.misc, rk)[M_VOTE + 8 * par + crk] = rebuild; peer(S.misc, rk)[M_CFAIL + 8 * par + crk] = S.misc[M_FAIL]; }
+                csync();
+                rebuild = 0;
+                int cf = 0;
+                for (int rk = 0; rk < csize(); rk++) { rebuild |= S.misc[M_VOTE + 8 * par + rk]; cf |= S.misc[M_CFAIL + 8 * par + rk]; }
+                __syncthreads();
+                if (tid == 0) { S.misc[M_FAIL] = S.misc[M_FAIL] | cf; if (it < d.n_steps) S.misc[M_PARITY] = S.misc[M_PARITY] ^ 1; }
+                __syncthreads();
+            }
 #endif
             ago++;
             rebuild = rebuild && (ago >= delay);
+#if ESB_CLUSTER
+            if (rebuild && !S.misc[M_FAIL] && it < d.n_steps) publish_velocities<NP>(a);   // the build's barriers come before the next per-atom phase
+#endif
             rs.eval++;
             ESB_TICK(t_atom)
             failed = S.misc[M_FAIL];
@@ -1380,6 +1442,10 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             }
         }
         const unsigned long long n_pairs = (unsigned int)S.misc[M_PAIRS];
+#if ESB_CLUSTER
+        publish_velocities<NP>(a);
+        csync();                                                             // rank 0 stores the state: it needs every bead's velocity
+#endif
         if (SEG) { rs.ago = ago; rs.rebuild = rebuild; rs.curlist = S.misc[M_CURLIST]; }
         if (crk == 0) {                                                      // (cluster variant: every CTA holds the same state; one of them reports)
         if (last_seg && !failed && d.observe) observe<NP>(a, r, d, rs, delt, sig_nm, c);
@@ -1396,8 +1462,13 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         }
         if (crk != 0) continue;
 #endif
+#if ESB_CLUSTER
+        const float4 *pos_now = carve<NP>(a).pos;                            // whichever buffer is current
+#else
+        const float4 *pos_now = S.pos;
+#endif
         for (int k = tid; k < np; k += ESB_THREADS) {
-            a.pos4[(size_t)r * np + k] = S.pos[k];
+            a.pos4[(size_t)r * np + k] = pos_now[k];
             a.vel4[(size_t)r * np + k] = make_float4(S.vx[k], S.vy[k], S.vz[k], 0.0f);
             if (SEG && !last_seg) a.bref4[(size_t)r * np + k] = make_float4(S.bx[k], S.by[k], S.bz[k], 0.0f);
         }
@@ -1453,11 +1524,15 @@ esb_forces_kernel(const __grid_constant__ KArgs a, const int pair_mode, const in
     double en[3] = {0.0, 0.0, 0.0};
     if (pair_mode == 1) force_phase<NP, 1, true>(a, r, soft_a, (float)rs.r0[1], (float)rs.r0[2], en);
     else if (pair_mode == 2) force_phase<NP, 2, true>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], en);
-    else { double eb = 0.0, ea = 0.0; bonded_forces<true>(S, a, r, (float)rs.r0[1], (float)rs.r0[2], eb, ea); en[1] = eb; en[2] = ea; }
+    else {
+        double eb = 0.0, ea = 0.0;
+        bonded_forces<true>(S, a, r, (float)rs.r0[1], (float)rs.r0[2], eb, ea); en[1] = eb; en[2] = ea;
+        for (int k = tid; k < np; k += ESB_THREADS) { S.fx[k] = 0.0f; S.fy[k] = 0.0f; S.fz[k] = 0.0f; }
+    }
     __syncthreads();
     double e_wall = 0.0;
     for (int i = tid; i < a.n_atoms; i += ESB_THREADS) {
-        float fx = S.fx[i], fy = S.fy[i], fz = S.fz[i];
+        float fx = S.gx[i] + S.fx[i], fy = S.gy[i] + S.fy[i], fz = S.gz[i] + S.fz[i];
         if (with_post) {
             const int fail = post_force<true>(a, i, S.pos[i], S.vx[i], S.vy[i], S.vz[i], fx, fy, fz, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), eval, e_wall);
             if (fail) atomicOr(&S.misc[M_FAIL], fail);
