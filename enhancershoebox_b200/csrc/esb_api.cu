@@ -126,6 +126,7 @@ struct esb_handle {
     int mic_n[3] = {0, 0, 0}, mic_frames = 0;
     unsigned short *d_mic = nullptr;
     int n_sm = 148;
+    size_t smem_per_sm = 233472;
     Layout lay = {0, 0, 0, 0};
     std::vector<ReplicaScalars> rs_host;
     int nry = 1, nrz = 1, qcx = 1, qcy = 1, qcz = 1;
@@ -344,7 +345,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     if (rc) return rc;
     CK(cudaSetDevice(device));
     esb_handle *h = new esb_handle();
-    { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, device) == cudaSuccess) h->n_sm = p.multiProcessorCount; }
+    { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, device) == cudaSuccess) { h->n_sm = p.multiProcessorCount; h->smem_per_sm = p.sharedMemPerMultiprocessor; } }
     h->device = device; h->R = n_replicas; h->N = n_atoms; h->n_types = n_types;
     h->n_pad = (n_atoms + 31) & ~31;
     if (const char *s = getenv("ESB_SKIN")) h->skin = atof(s);
@@ -927,11 +928,13 @@ int esb_run(esb_handle *h, int chunk_begin, int n_chunks, void *stream)
     fill_kargs(h, k, false);
     // a batch that cannot fill the device with two CTAs per SM gets the 32-warp CTA: a replica then advances twice as fast
     const int n_seg = getenv("ESB_SEG") ? atoi(getenv("ESB_SEG")) : 0;      // 0: the launcher decides
-    const bool wide = getenv("ESB_WIDE") ? atoi(getenv("ESB_WIDE")) != 0 : h->R <= h->n_sm;
+    // (also a system too large for two 16-warp CTAs per SM -- more than ~1700 beads: one 32-warp CTA fills the SM better than one 16-warp CTA)
+    const bool two_fit = 2 * (smem + 1024) <= h->smem_per_sm;
+    const bool wide = getenv("ESB_WIDE") ? atoi(getenv("ESB_WIDE")) != 0 : (h->R <= h->n_sm || !two_fit);
     // even smaller batches: a thread-block cluster of 2, 4 or 8 CTAs (SMs) per replica
     int cluster = 1;
     if (getenv("ESB_CLUSTER_SIZE")) cluster = atoi(getenv("ESB_CLUSTER_SIZE"));
-    else if (wide) for (int c = 4; c >= 2; c >>= 1) if ((long long)h->R * c <= (long long)h->n_sm * 7 / 8) { cluster = c; break; }   // (8 measured slower than 4)
+    else if (wide && h->R <= h->n_sm) for (int c = 8; c >= 2; c >>= 1) if ((long long)h->R * c <= (long long)h->n_sm * 7 / 8) { cluster = c; break; }
     if (cluster == 2 || cluster == 4 || cluster == 8) {
         const size_t smem_c = esb_smem_bytes_v2048(h->n_pad, (int)h->tables.size());
         CK(esb_launch_run_v2048(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem_c, (cudaStream_t)stream, h->d_sched, h->n_sm, cluster));

@@ -47,3 +47,25 @@ def test_cluster_of_ctas_per_replica_is_bitwise_identical(box11, snapshots, monk
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a, b)
     assert np.all(out[0][4] == 0) and np.all(out[0][5] == 600)
+
+
+def test_wide_ctas_with_more_replicas_than_sms_are_bitwise_identical(box11, snapshots, monkeypatch):
+    """The 32-warp CTA (one per SM) is also the kernel of systems too large for two 16-warp CTAs per SM, whatever
+    the batch size: with more replicas than SMs it walks the same ticket ring as the 16-warp kernel."""
+    x, v, t = snapshots["x500"].astype(np.float64), snapshots["v500"].astype(np.float64), snapshots["t500"].astype(np.int32)
+    plans = P.chunk_schedule("genes_stages", n_chunks=503)[500:]
+    R = 170
+    out = []
+    for wide in (0, 1):
+        monkeypatch.setenv("ESB_WIDE", str(wide))
+        eng = E.ShoeboxBatch(box11, n_replicas=R, seeds=np.arange(R) + 11, thresholds=20, activations=100)
+        eng.upload_state(x[None], v[None], t[None], replicate=True)
+        eng.set_schedule(plans=plans, observe=True)
+        eng.run(0, 2)
+        eng.run(2, 1)
+        c = eng.counters()
+        out.append(eng.state() + (eng.frames(), eng.status(), c["steps"], c["builds"], c["evals"], c["dangerous"], c["listed"], c["pairs"]))
+        eng.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    assert np.all(out[0][4] == 0) and np.all(out[0][5] == 600)
