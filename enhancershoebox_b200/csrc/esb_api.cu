@@ -909,7 +909,7 @@ static int prepare_launch(esb_handle *h, size_t *smem)
     if ((size_t)12 * h->n_pad < (size_t)(ESB_NL_MAXNB + 1) * 4)
         return fail(ESB_EINVAL, "replica of %d atoms is too small: the list build keeps %d counters in the force arrays (>= %d beads)",
                     h->N, ESB_NL_MAXNB + 1, (ESB_NL_MAXNB + 1) / 3 + 1);
-    *smem = esb_smem_bytes_v512(h->n_pad, (int)h->tables.size());
+    *smem = esb_smem_bytes_v512(h->n_pad, (int)h->tables.size(), h->n_topo_pad);
     if (*smem > 227 * 1024) return fail(ESB_EINVAL, "replica of %d atoms needs %zu B of shared memory (max 232448)", h->N, *smem);
     return ESB_OK;
 }
@@ -936,10 +936,10 @@ int esb_run(esb_handle *h, int chunk_begin, int n_chunks, void *stream)
     if (getenv("ESB_CLUSTER_SIZE")) cluster = atoi(getenv("ESB_CLUSTER_SIZE"));
     else if (wide && h->R <= h->n_sm) for (int c = 8; c >= 2; c >>= 1) if ((long long)h->R * c <= (long long)h->n_sm * 7 / 8) { cluster = c; break; }
     if (cluster == 2 || cluster == 4 || cluster == 8) {
-        const size_t smem_c = esb_smem_bytes_v2048(h->n_pad, (int)h->tables.size());
+        const size_t smem_c = esb_smem_bytes_v2048(h->n_pad, (int)h->tables.size(), h->n_topo_pad);
         CK(esb_launch_run_v2048(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem_c, (cudaStream_t)stream, h->d_sched, h->n_sm, cluster));
     } else if (wide) {
-        const size_t smem_w = esb_smem_bytes_v1024(h->n_pad, (int)h->tables.size());
+        const size_t smem_w = esb_smem_bytes_v1024(h->n_pad, (int)h->tables.size(), h->n_topo_pad);
         CK(esb_launch_run_v1024(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem_w, (cudaStream_t)stream, h->d_sched, h->n_sm, n_seg));
     } else {
         CK(esb_launch_run_v512(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem, (cudaStream_t)stream, h->d_sched, h->n_sm, n_seg));

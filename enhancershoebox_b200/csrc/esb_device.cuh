@@ -162,9 +162,9 @@ __device__ __forceinline__ float u32_centered(uint32_t u) { return (float)(int32
 #define ESB_CAT2_(a, b) a##b
 #define ESB_CAT2(a, b) ESB_CAT2_(a, b)
 #define ESB_VARIANT(name) ESB_CAT2(name##_v, ESB_TAG)
-size_t esb_smem_bytes_v512(int n_pad, int n_tables);
-size_t esb_smem_bytes_v1024(int n_pad, int n_tables);
-size_t esb_smem_bytes_v2048(int n_pad, int n_tables);
+size_t esb_smem_bytes_v512(int n_pad, int n_tables, int n_topo_pad);
+size_t esb_smem_bytes_v1024(int n_pad, int n_tables, int n_topo_pad);
+size_t esb_smem_bytes_v2048(int n_pad, int n_tables, int n_topo_pad);
 cudaError_t esb_launch_run_v2048(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,
                                  int *sched, int n_sm, int cluster_size);
 cudaError_t esb_launch_run_v512(const KArgs &k, int chunk_begin, int n_chunks, double delt, double sig_nm, size_t smem, cudaStream_t st,

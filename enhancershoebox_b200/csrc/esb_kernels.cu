@@ -46,7 +46,8 @@ struct Smem {
     float4 *pos;                 // x, y, z, (type | frozen << 8) as int bits
     float *vx, *vy, *vz;
     float *fx, *fy, *fz;         // pair forces; the same bytes serve as scratch during a list build
-    float *gx, *gy, *gz;         // bonded forces (own arrays: the bonded pass and the pair loop run without a barrier between them)
+    float *gx, *gy, *gz;         // [n_topo_pad] bonded forces of the beads that have bonded terms (own arrays: the bonded pass and
+                                 // the pair loop run without a barrier between them); last in the layout: the only run-time offsets
     float *bx, *by, *bz;         // positions at the last neighbour build
     PairSetup *setup;
     DevTab *tab;
@@ -72,11 +73,12 @@ enum { M_QCTR = 0 /* next quad of the running build / force loop */, M_FAIL, M_P
 #endif
 enum { D_RR = 0, D_PROBE = 3, D_GENE = 6, D_END = 10 };
 
-__host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables)
+__host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables, int n_topo_pad)
 {
     size_t b = 0;
     b += (size_t)n_pad * 16;                 // pos
-    b += (size_t)n_pad * 4 * 12;             // v, f (pair), f (bonded), xbuild
+    b += (size_t)n_pad * 4 * 9;              // v, f (pair), xbuild
+    b += (size_t)n_topo_pad * 4 * 3 + 16;    // f (bonded), behind everything else (16-byte aligned)
     b += (sizeof(PairSetup) + 15) & ~(size_t)15;
     b += ((size_t)n_tables * sizeof(DevTab) + 15) & ~(size_t)15;
     b += ((size_t)M_END * 4 + 15) & ~(size_t)15;
@@ -106,9 +108,6 @@ __device__ __forceinline__ Smem carve(const KArgs &a, const bool first_buffer = 
     S.fx = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.fy = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.fz = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
-    S.gx = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
-    S.gy = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
-    S.gz = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.bx = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.by = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
     S.bz = reinterpret_cast<float *>(base + o); o += (size_t)np * 4;
@@ -127,6 +126,13 @@ __device__ __forceinline__ Smem carve(const KArgs &a, const bool first_buffer = 
         S.mine = reinterpret_cast<unsigned short *>(base + o + (size_t)np * 16);
     }
 #endif
+#if ESB_CLUSTER
+    o += (size_t)np * 16 + (size_t)np * 2;
+#endif
+    o = (o + 15) & ~(size_t)15;
+    S.gx = reinterpret_cast<float *>(base + o);
+    S.gy = S.gx + a.n_topo_pad;
+    S.gz = S.gy + a.n_topo_pad;
     S.cend = reinterpret_cast<unsigned short *>(S.fx);
     S.sidx = S.cend + ((a.nrows * ESB_NCLASS + 2 + 7) & ~7);
     S.xs = reinterpret_cast<float *>(S.sidx + 2 * np);
@@ -162,7 +168,7 @@ template <int NP>
 __device__ __forceinline__ int tab_off4(const KArgs &a)
 {
     const int np = NP ? NP : a.n_pad;
-    return (np * 64 + (int)((sizeof(PairSetup) + 15) & ~(size_t)15)) / 16;   // float4 index of S.tab
+    return (np * 52 + (int)((sizeof(PairSetup) + 15) & ~(size_t)15)) / 16;   // float4 index of S.tab
 }
 
 __device__ __forceinline__ int cell_coord(float x, float lo, float inv, int n)
@@ -543,7 +549,7 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
     for (int k = threadIdx.x; k < S.misc[M_NMINE]; k += ESB_THREADS) {   // the other beads belong to other CTAs of the cluster
         const int i = S.mine[k];
 #else
-    for (int i = threadIdx.x; i < n; i += ESB_THREADS) {
+    for (int i = threadIdx.x; i < n_topo; i += ESB_THREADS) {
 #endif
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
         if (i < n_topo) {
@@ -593,8 +599,9 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
                 }
             }
         }
-        S.gx[i] = fx; S.gy[i] = fy; S.gz[i] = fz;
+        if (i < n_topo) { S.gx[i] = fx; S.gy[i] = fy; S.gz[i] = fz; }
     }
+    (void)n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -807,7 +814,8 @@ __device__ __noinline__ int atom_phase(const KArgs &a, const bool do_final, cons
 #endif
         float4 p = S.pos[i];
         float vx = S.vx[i], vy = S.vy[i], vz = S.vz[i];
-        float fx = S.gx[i] + S.fx[i], fy = S.gy[i] + S.fy[i], fz = S.gz[i] + S.fz[i];    // bonded + pair
+        const bool topo = i < a.n_topo;
+        float fx = (topo ? S.gx[i] : 0.0f) + S.fx[i], fy = (topo ? S.gy[i] : 0.0f) + S.fy[i], fz = (topo ? S.gz[i] : 0.0f) + S.fz[i];    // bonded + pair
         const int fail = post_force<false>(a, i, p, vx, vy, vz, fx, fy, fz, k0, k1, eval, dummy);
         if (fail) atomicOr(&S.misc[M_FAIL], fail);
         if (do_final) { vx += dtf * fx; vy += dtf * fy; vz += dtf * fz; }
@@ -1532,7 +1540,8 @@ esb_forces_kernel(const __grid_constant__ KArgs a, const int pair_mode, const in
     __syncthreads();
     double e_wall = 0.0;
     for (int i = tid; i < a.n_atoms; i += ESB_THREADS) {
-        float fx = S.gx[i] + S.fx[i], fy = S.gy[i] + S.fy[i], fz = S.gz[i] + S.fz[i];
+        const bool topo = i < a.n_topo;
+        float fx = (topo ? S.gx[i] : 0.0f) + S.fx[i], fy = (topo ? S.gy[i] : 0.0f) + S.fy[i], fz = (topo ? S.gz[i] : 0.0f) + S.fz[i];
         if (with_post) {
             const int fail = post_force<true>(a, i, S.pos[i], S.vx[i], S.vy[i], S.vz[i], fx, fy, fz, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), eval, e_wall);
             if (fail) atomicOr(&S.misc[M_FAIL], fail);
@@ -1587,7 +1596,7 @@ extern "C" __global__ void esb_unpack_kernel(const float4 *pos4, const float4 *v
 
 #endif   // ESB_TAG == 512 (parity hook and the pack/unpack kernels exist once)
 
-size_t ESB_VARIANT(esb_smem_bytes)(int n_pad, int n_tables) { return smem_bytes_for(n_pad, n_tables); }
+size_t ESB_VARIANT(esb_smem_bytes)(int n_pad, int n_tables, int n_topo_pad) { return smem_bytes_for(n_pad, n_tables, n_topo_pad); }
 
 // Host launchers: the kernels are instantiated for the bead capacities of the reference's box sizes
 // (box 9..12 without actin: 1050/1172/1290/1400 beads -> 1056/1184/1312/1408; box 11 with actin:
