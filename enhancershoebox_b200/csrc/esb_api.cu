@@ -309,6 +309,8 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     k.n_tables = (int)h->tables.size();
     k.tabval = h->d_tabval; k.tabe = h->d_tabe; k.tlm1 = h->tlm1;
     k.nl_pool = h->d_nl_pool; k.nl_qinfo = h->d_nl_qinfo;
+    // 16-bit list entries need the table id in 5 bits and the bead index in 11 (always true: n_pad <= ESB_NL_STRIDE)
+    k.pack16 = getenv("ESB_PACK16") ? atoi(getenv("ESB_PACK16")) != 0 && h->tables.size() <= 32 : h->tables.size() <= 32;
     memcpy(k.class_of, k_class_of, ESB_MAXT);
     k.descs = h->d_descs;
     k.lay = h->lay; k.enh_idx = h->d_enh; k.s5p_idx = h->d_s5p; k.cluster_r = h->d_cluster_r;
@@ -339,8 +341,8 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
 {
     if (!out) return fail(ESB_EINVAL, "out is NULL");
     *out = nullptr;
-    if (n_replicas < 1 || n_atoms < 1 || n_atoms > 65535 || n_types < 1 || n_types >= ESB_MAXT)
-        return fail(ESB_EINVAL, "bad sizes: replicas=%d atoms=%d (max 65535) types=%d (max %d)", n_replicas, n_atoms, n_types, ESB_MAXT - 1);
+    if (n_replicas < 1 || n_atoms < 1 || n_atoms > ESB_NL_STRIDE || n_types < 1 || n_types >= ESB_MAXT)
+        return fail(ESB_EINVAL, "bad sizes: replicas=%d atoms=%d (max %d) types=%d (max %d)", n_replicas, n_atoms, ESB_NL_STRIDE, n_types, ESB_MAXT - 1);
     int rc = check_device(device);
     if (rc) return rc;
     CK(cudaSetDevice(device));

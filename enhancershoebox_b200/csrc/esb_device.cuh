@@ -23,7 +23,9 @@
 #define ESB_MAX_TERMS 8              // bonded terms per atom (linear chain: 2 bonds + 3 angles)
 #define ESB_MAX_SPEC 8               // excluded partners per atom (linear chain: 6)
 #define ESB_NL_MAXNB 2047            // neighbours per atom in the full list (16-bit count in the descriptor); every
+#ifndef ESB_NL_STRIDE
 #define ESB_NL_STRIDE 2048           // bead owns an arena of this many entries: a system of up to 2048 beads cannot
+#endif
                                      // overflow it (LAMMPS: neigh_modify one 10000 page 100000, run_single_shoebox.py:533)
 #define ESB_NCLASS 6                 // species classes for the row sort: chromatin-like, actin, RBP, RNP, Ser5P, gene body (induced/active)
 #define ESB_N_COUNTERS 11             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases, dangerous builds
@@ -118,7 +120,8 @@ struct KArgs {
     const float *tabval;      // patch / array values (F/r), fp32
     const float *tabe;        // energy arrays (hook)
     int tlm1;
-    unsigned int *nl_pool;    // [R][n_pad][ESB_NL_STRIDE]  neighbour index | table id << 16
+    unsigned int *nl_pool;    // [R][n_pad][ESB_NL_STRIDE]  neighbour index | table id << 16; or two 16-bit entries per word:
+    int pack16;               // 1: 16-bit list entries (neighbour index | table id << 11), possible with at most 32 tables
     uint2 *nl_qinfo;          // [R][2][n_pad] {list start, atom | count << 16}: [0] sorted by list length (force order), [1] slot order (build)
     unsigned char class_of[ESB_MAXT + 4];
     const esb_chunk_desc *descs;

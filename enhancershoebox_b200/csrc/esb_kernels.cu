@@ -251,7 +251,7 @@ __device__ __forceinline__ void slot_sort(const Smem &S, const KArgs &a, const i
 // order is a function of the positions only).  Afterwards the descriptors are re-sorted by list
 // length: that is the order in which the force loop forms its quads.
 // ------------------------------------------------------------------------------------------------
-template <int NP>
+template <int NP, bool P16>
 __device__ __noinline__ void build_lists(const KArgs &a, const int r)
 {
     const Smem S = carve<NP>(a);
@@ -305,7 +305,12 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
 
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESB_NL_STRIDE;
+    // P16 (at most 32 tables): 16-bit entries (neighbour | table id << 11), two per word -- word 8*(e/16) + e%8 holds
+    // entries e (low half) and e + 8 (high half) of a block of 16, so that lane g of a bead's group reads its entries
+    // g and g + 8 with one load and sums in the same order as with 32-bit entries; half the list traffic
+    constexpr unsigned int ESTRIDE = P16 ? ESB_NL_STRIDE / 2 : ESB_NL_STRIDE;      // arena of a bead in words
+    unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESTRIDE;
+    unsigned short *pool16 = reinterpret_cast<unsigned short *>(pool);
     uint2 *qbuild = a.nl_qinfo + ((size_t)r * 2 + 1) * a.n_pad;     // descriptors in build (sorted) order
     const float loy = a.lo[1], loz = a.lo[2], rinv = a.row_inv;
     const int n_topo = a.n_topo;
@@ -427,7 +432,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
                     unsigned int ent_u = 0u;
                     if (UNIFORM) {
                         cs_u = cs_row[ta[0] * ESB_MAXT + tj];
-                        ent_u = (unsigned int)j | ((unsigned int)tab_row[ta[0] * ESB_MAXT + tj] << 16);
+                        ent_u = (unsigned int)j | ((unsigned int)tab_row[ta[0] * ESB_MAXT + tj] << (P16 ? 11 : 16));
                     }
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
@@ -446,8 +451,11 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
                         const unsigned int bits = __ballot_sync(FULL, ok);
                         if (bits) {                                  // warp-uniform: most candidates are rejected by every bead
                             const int at = cnt[b] + __popc(bits & lt_mask);
-                            if (ok && at < ESB_NL_MAXNB)
-                                pool[(unsigned int)ia[b] * ESB_NL_STRIDE + at] = UNIFORM ? ent_u : ((unsigned int)j | ((unsigned int)tab_row[ta[b] * ESB_MAXT + tj] << 16));
+                            if (ok && at < ESB_NL_MAXNB) {
+                                if (P16) pool16[(unsigned int)ia[b] * ESB_NL_STRIDE + ((at & ~15) | ((at & 7) << 1) | ((at >> 3) & 1))] =
+                                             (unsigned short)(UNIFORM ? ent_u : ((unsigned int)j | ((unsigned int)tab_row[ta[b] * ESB_MAXT + tj] << 11)));
+                                else pool[(unsigned int)ia[b] * ESB_NL_STRIDE + at] = UNIFORM ? ent_u : ((unsigned int)j | ((unsigned int)tab_row[ta[b] * ESB_MAXT + tj] << 16));
+                            }
                             cnt[b] += __popc(bits);
                         }
                     }
@@ -464,7 +472,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
             const int i = lane == 0 ? ia[0] : lane == 1 ? ia[1] : lane == 2 ? ia[2] : ia[3];
             if (idx < n) {
                 if (c > ESB_NL_MAXNB) { atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH); c = ESB_NL_MAXNB; }
-                qbuild[idx] = make_uint2((unsigned int)i * ESB_NL_STRIDE, (unsigned int)i | ((unsigned int)c << 16));
+                qbuild[idx] = make_uint2((unsigned int)i * ESTRIDE, (unsigned int)i | ((unsigned int)c << 16));
                 listed += c;
             }
         }
@@ -616,7 +624,7 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
 //         the bin midpoint (ljsoft_potential.py:10-16) inside [p0hi, plo) and the LOOKUP array
 //         entry elsewhere.
 // ------------------------------------------------------------------------------------------------
-template <int NP, int MODE, bool ENERGY>
+template <int NP, int MODE, bool ENERGY, bool P16>
 __device__ __noinline__ void force_phase(const KArgs &a, const int r, const float soft_a, const float r0_1, const float r0_2,
                                          double *energy /* [3] pair, bond, angle: per-thread partials (ENERGY only) */)
 {
@@ -629,7 +637,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
     // no barrier between the two: the bonded pass writes S.g*, the pair loop S.f*; a warp whose beads have no
     // bonded terms starts on the quads while the others wait for their term rows.  (S.misc[M_QCTR] is 0 on entry.)
     bonded_forces<ENERGY>(S, a, r, r0_1, r0_2, e_bond, e_angle);
-    const unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESB_NL_STRIDE;
+    const unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * (P16 ? ESB_NL_STRIDE / 2 : ESB_NL_STRIDE);
     const uint2 *qinfo = a.nl_qinfo + (size_t)r * 2 * a.n_pad;
 #if ESB_CLUSTER
     const unsigned int sb0 = smem_base(), tbase = sb0 + 16u * (unsigned int)tab_off4<NP>(a);
@@ -669,7 +677,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
         const unsigned int *lp = nl + gl;
         auto pair_body = [&](const unsigned int ent, const int e) {
             if (e < cnt) {
-                const float4 pj = lds128(sb + 16u * (ent & 0xffffu));
+                const float4 pj = lds128(sb + 16u * (ent & (P16 ? 0x7ffu : 0xffffu)));
                 const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 const float r2 = dx * dx + dy * dy + dz * dz;
                 float fpair;
@@ -684,7 +692,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                     if (ENERGY) e_pair += 0.5 * (double)(soft_a * (1.0f + cospif(xr)));
                     npairs++;
                 } else {
-                    const unsigned int tb = ent >> 16;                          // table id of the pair (fixed between builds)
+                    const unsigned int tb = P16 ? (ent >> 11) & 0x1fu : ent >> 16;   // table id of the pair (fixed between builds)
                     const unsigned int T4 = tbase + 48u * tb;                         // DevTab = 3 float4 words
                     const float4 t0 = lds128(T4);                                     // cutsq, invdelta_f, delta, innersq_f
                     if (!(r2 < t0.x)) return;
@@ -719,18 +727,32 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                 fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
             }
         };
-        constexpr int DEPTH = ESB_PREFETCH;                       // list entries in flight per lane
+        constexpr int DEPTH = ESB_PREFETCH;                       // list words in flight per lane
         unsigned int w[DEPTH];
 #pragma unroll
         for (int k = 0; k < DEPTH; k++) w[k] = __ldcg(lp + k * ESB_G);
-        for (int e0 = 0; e0 < cnt_max; e0 += DEPTH * ESB_G) {
-            lp += DEPTH * ESB_G;
+        if (P16) {                                                // one word = the lane's entries e0 + gl and e0 + 8 + gl
+            static_assert(ESB_G == 8, "16-bit list layout: blocks of 2 x 8 entries");
+            for (int e0 = 0; e0 < cnt_max; e0 += DEPTH * 2 * ESB_G) {
+                lp += DEPTH * ESB_G;
 #pragma unroll
-            for (int k = 0; k < DEPTH; k += 2) {
-                if (k > 0 && e0 + k * ESB_G >= cnt_max) break;
-                const unsigned int c0 = w[k], c1 = w[k + 1];
-                w[k] = __ldcg(lp + k * ESB_G); w[k + 1] = __ldcg(lp + (k + 1) * ESB_G);
-                pair_body(c0, e0 + k * ESB_G + gl); pair_body(c1, e0 + (k + 1) * ESB_G + gl);
+                for (int k = 0; k < DEPTH; k++) {
+                    if (k > 0 && e0 + k * 2 * ESB_G >= cnt_max) break;
+                    const unsigned int c = w[k];
+                    w[k] = __ldcg(lp + k * ESB_G);
+                    pair_body(c, e0 + k * 2 * ESB_G + gl); pair_body(c >> 16, e0 + (2 * k + 1) * ESB_G + gl);
+                }
+            }
+        } else {
+            for (int e0 = 0; e0 < cnt_max; e0 += DEPTH * ESB_G) {
+                lp += DEPTH * ESB_G;
+#pragma unroll
+                for (int k = 0; k < DEPTH; k += 2) {
+                    if (k > 0 && e0 + k * ESB_G >= cnt_max) break;
+                    const unsigned int c0 = w[k], c1 = w[k + 1];
+                    w[k] = __ldcg(lp + k * ESB_G); w[k + 1] = __ldcg(lp + (k + 1) * ESB_G);
+                    pair_body(c0, e0 + k * ESB_G + gl); pair_body(c1, e0 + (k + 1) * ESB_G + gl);
+                }
             }
         }
 #pragma unroll
@@ -1303,7 +1325,7 @@ __device__ __noinline__ void actin_events(const KArgs &a, const int r, const esb
 // number of co-resident CTAs, so a waiting CTA's producer is always running.
 // (own namespace per compiled variant: the two instantiations must not be merged by the linker)
 namespace ESB_VARIANT(esb_step) {
-template <int NP, bool SEG>
+template <int NP, bool SEG, bool P16>
 __global__ void __launch_bounds__(ESB_THREADS, ESB_MIN_CTAS)
 esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int n_chunks, const int n_seg_arg, const double delt, const double sig_nm,
                int *ticket, int *progress)
@@ -1405,9 +1427,9 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         const int delay = max(a.neigh_delay, 1);
         const bool last_seg = SEG ? it1 == d.n_steps + 1 : true;
         for (int it = it0; it < it1; it++) {
-            if (rebuild) { build_lists<NP>(a, r); n_builds++; if (ago == delay) n_danger++; ago = 0; ESB_TICK(t_build) }
-            if (d.pair_mode == 1) force_phase<NP, 1, false>(a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
-            else force_phase<NP, 2, false>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
+            if (rebuild) { build_lists<NP, P16>(a, r); n_builds++; if (ago == delay) n_danger++; ago = 0; ESB_TICK(t_build) }
+            if (d.pair_mode == 1) force_phase<NP, 1, false, P16>(a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
+            else force_phase<NP, 2, false, P16>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
             n_evals++;
             __syncthreads();
             if (tid == 0) S.misc[M_QCTR] = 0;                        // (visible to the next force loop through the per-atom phase's barrier)
@@ -1528,10 +1550,10 @@ esb_forces_kernel(const __grid_constant__ KArgs a, const int pair_mode, const in
         for (int k = tid; k < (int)(sizeof(PairSetup) / 4); k += ESB_THREADS) dst[k] = src[k];
     }
     __syncthreads();
-    build_lists<NP>(a, r);
+    build_lists<NP, false>(a, r);
     double en[3] = {0.0, 0.0, 0.0};
-    if (pair_mode == 1) force_phase<NP, 1, true>(a, r, soft_a, (float)rs.r0[1], (float)rs.r0[2], en);
-    else if (pair_mode == 2) force_phase<NP, 2, true>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], en);
+    if (pair_mode == 1) force_phase<NP, 1, true, false>(a, r, soft_a, (float)rs.r0[1], (float)rs.r0[2], en);
+    else if (pair_mode == 2) force_phase<NP, 2, true, false>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], en);
     else {
         double eb = 0.0, ea = 0.0;
         bonded_forces<true>(S, a, r, (float)rs.r0[1], (float)rs.r0[2], eb, ea); en[1] = eb; en[2] = ea;
@@ -1620,7 +1642,7 @@ cudaError_t ESB_VARIANT(esb_launch_run)(const KArgs &k, int chunk_begin, int n_c
     (void)n_sm;
     cudaError_t e = cudaSuccess;
     ESB_FOR_NP(k.n_pad, {
-        auto kern = esb_run_kernel<NPC, false>;
+        auto kern = k.pack16 ? esb_run_kernel<NPC, false, true> : esb_run_kernel<NPC, false, false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute attr[1];
@@ -1645,9 +1667,11 @@ cudaError_t ESB_VARIANT(esb_launch_run)(const KArgs &k, int chunk_begin, int n_c
 {
     cudaError_t e = cudaSuccess;
     ESB_FOR_NP(k.n_pad, {
-        e = cudaFuncSetAttribute(esb_run_kernel<NPC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = k.pack16 ? esb_run_kernel<NPC, false, true> : esb_run_kernel<NPC, false, false>;
+        auto kern_seg = k.pack16 ? esb_run_kernel<NPC, true, true> : esb_run_kernel<NPC, true, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, esb_run_kernel<NPC, false>, ESB_THREADS, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ESB_THREADS, smem);
         if (e == cudaSuccess && per_sm < 1) e = cudaErrorLaunchOutOfResources;
         if (e == cudaSuccess) e = cudaMemsetAsync(sched, 0, sizeof(int) * (size_t)(1 + k.n_replicas), st);
         if (e == cudaSuccess) {
@@ -1659,10 +1683,10 @@ cudaError_t ESB_VARIANT(esb_launch_run)(const KArgs &k, int chunk_begin, int n_c
                 n_seg = (k.n_replicas <= grid || k.n_replicas % grid == 0 || items >= 8LL * grid) ? 1 : (items < 3LL * grid ? 8 : 4);
             }
             if (n_seg > 1) {
-                e = cudaFuncSetAttribute(esb_run_kernel<NPC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e == cudaSuccess) esb_run_kernel<NPC, true><<<grid, ESB_THREADS, smem, st>>>(k, chunk_begin, n_chunks, n_seg, delt, sig_nm, sched, sched + 1);
+                e = cudaFuncSetAttribute(kern_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e == cudaSuccess) kern_seg<<<grid, ESB_THREADS, smem, st>>>(k, chunk_begin, n_chunks, n_seg, delt, sig_nm, sched, sched + 1);
             } else {
-                esb_run_kernel<NPC, false><<<grid, ESB_THREADS, smem, st>>>(k, chunk_begin, n_chunks, 1, delt, sig_nm, sched, sched + 1);
+                kern<<<grid, ESB_THREADS, smem, st>>>(k, chunk_begin, n_chunks, 1, delt, sig_nm, sched, sched + 1);
             }
             e = cudaGetLastError();
         }

@@ -69,3 +69,24 @@ def test_wide_ctas_with_more_replicas_than_sms_are_bitwise_identical(box11, snap
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a, b)
     assert np.all(out[0][4] == 0) and np.all(out[0][5] == 600)
+
+
+def test_16_bit_list_entries_are_bitwise_identical(box11, snapshots, monkeypatch):
+    """With at most 32 tables the neighbour lists hold 16-bit entries, two per word, laid out so that every lane sums
+    its neighbours in the order of the 32-bit lists: same trajectory, same counters, half the list traffic."""
+    x, v, t = snapshots["x500"].astype(np.float64), snapshots["v500"].astype(np.float64), snapshots["t500"].astype(np.int32)
+    plans = P.chunk_schedule("genes_stages", n_chunks=503)[500:]
+    out = []
+    for packed in (0, 1):
+        monkeypatch.setenv("ESB_PACK16", str(packed))
+        eng = E.ShoeboxBatch(box11, n_replicas=5, seeds=[3, 4, 5, 6, 7], thresholds=20, activations=100)
+        eng.upload_state(x[None], v[None], t[None], replicate=True)
+        eng.set_schedule(plans=plans, observe=True)
+        eng.run(0, 2)
+        eng.run(2, 1)
+        c = eng.counters()
+        out.append(eng.state() + (eng.frames(), eng.status(), c["steps"], c["builds"], c["evals"], c["dangerous"], c["listed"], c["pairs"]))
+        eng.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    assert np.all(out[0][4] == 0) and np.all(out[0][5] == 600)
