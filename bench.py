@@ -273,7 +273,7 @@ def run_native(args, w):
             "metric": "replica_timesteps_per_s", "value": value, "unit": "replica-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "replicas_per_gpu": R, "n_atoms": d.n_atoms, "md_steps_per_step": T_RUN,
-                       "start_chunk": START_CHUNK, "l2": "state is SMEM-resident; the neighbour lists (~90 KB per replica and evaluation plus descriptors, rebuilt every 10 steps, 512 replicas in a ring) are larger than L2 together with their write traffic and stream from HBM/L2 (ncu: 12 % L2 misses)",
+                       "start_chunk": START_CHUNK, "l2": f"not flushed (the K steps are one persistent launch) and nothing is re-read across steps: a step reads the {2 * R * n_pad * 16 / 1e6:.0f} MB state once from HBM/L2, keeps it in shared memory for 200 MD steps, and rebuilds its own neighbour lists 21 times (~90 KB per replica and build, re-read 10 times from L2/HBM; ncu: 12 % L2 misses, 0.09 TB/s DRAM); the path is issue-bound, not memory-bound",
                        "neighbor": f"skin {P.NEIGH_SKIN} delay {P.NEIGH_DELAY} check yes (reference: run_single_shoebox.py:532-533)",
                        "parallelism": f"replicas sharded over {world} GPU(s), no collective on the step path"},
             "bead_steps_per_s": value * d.n_atoms,
