@@ -13,7 +13,7 @@
 #define ESB_THREADS 512
 #endif
 #ifndef ESB_PREFETCH
-#define ESB_PREFETCH 2                  // neighbour-list entries each lane keeps in flight (even); 2 is best with 16-warp CTAs
+#define ESB_PREFETCH 2                  // neighbour-list words each lane keeps in flight (even; 4 entries with 16-bit lists); 2 is best with 16-warp CTAs
 #endif
 #ifndef ESB_MIN_CTAS
 #define ESB_MIN_CTAS 2                  // resident CTAs per SM the step kernel is compiled for (2 x 16 warps: 64 registers)
