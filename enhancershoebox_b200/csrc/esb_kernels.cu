@@ -71,7 +71,10 @@ enum { M_QCTR = 0 /* next quad of the running build / force loop */, M_FAIL, M_P
 #else
        M_END = M_HIST + 52 };
 #endif
-enum { D_RR = 0, D_PROBE = 3, D_GENE = 6, D_END = 10 };
+enum { D_RR = 0, D_PROBE = 3, D_GENE = 6,
+       // per-chunk statistics, kept by thread 0 in shared memory (as 64-bit integers) instead of in registers of
+       // every thread: the chunk loop runs at the 64-register cap and would spill them to L2-backed local memory
+       L_EVALS = 10, L_BUILDS, L_STEPS, L_LISTED, L_DANGER, L_TATOM, L_TBUILD, L_TFORCE, L_TOBS, L_TMARK, D_END };
 
 __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables, int n_topo_pad)
 {
@@ -1392,9 +1395,9 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         }
         for (int k = tid; k < M_END; k += ESB_THREADS) S.misc[k] = (SEG && k == M_CURLIST && it0 > 0) ? rs.curlist : 0;
         const uint32_t k0 = (uint32_t)rs.seed, k1 = (uint32_t)(rs.seed >> 32);
-        unsigned long long n_evals = 0, n_builds = 0, n_steps_done = 0, n_listed = 0;
-        long long t_atom = 0, t_build = 0, t_force = 0, t_obs = 0, t_mark = clock64();
-#define ESB_TICK(acc) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; }
+        long long *const L = reinterpret_cast<long long *>(S.dmisc);          // L_* slots: touched by thread 0 only
+        if (tid == 0) { for (int k = L_EVALS; k < L_TMARK; k++) L[k] = 0; L[L_TMARK] = clock64(); }
+#define ESB_TICK(acc) { if (tid == 0) { const long long now_ = clock64(); L[acc] += now_ - L[L_TMARK]; L[L_TMARK] = now_; } }
         int failed = 0;
         const esb_chunk_desc d = a.descs[c];
         {
@@ -1418,23 +1421,21 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             }
         }
         __syncthreads();
-        ESB_TICK(t_obs)
+        ESB_TICK(L_TOBS)
         // [LAMMPS-ext] Neighbor::decide with `neigh_modify every 1 delay 10 check yes` (run_single_shoebox.py:533):
         // every run builds at set-up; afterwards a build needs `delay` steps since the last one AND a bead that
         // moved further than skin/2.  A build already due at the first permitted step is a "dangerous build".
         int rebuild = (!SEG || it0 == 0) ? 1 : rs.rebuild, ago = (!SEG || it0 == 0) ? 0 : rs.ago;
-        unsigned long long n_danger = 0;
         const int delay = max(a.neigh_delay, 1);
         const bool last_seg = SEG ? it1 == d.n_steps + 1 : true;
         for (int it = it0; it < it1; it++) {
-            if (rebuild) { build_lists<NP, P16>(a, r); n_builds++; if (ago == delay) n_danger++; ago = 0; ESB_TICK(t_build) }
+            if (rebuild) { build_lists<NP, P16>(a, r); if (tid == 0) { L[L_BUILDS]++; if (ago == delay) L[L_DANGER]++; } ago = 0; ESB_TICK(L_TBUILD) }
             if (d.pair_mode == 1) force_phase<NP, 1, false, P16>(a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
             else force_phase<NP, 2, false, P16>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
-            n_evals++;
             __syncthreads();
             if (tid == 0) S.misc[M_QCTR] = 0;                        // (visible to the next force loop through the per-atom phase's barrier)
-            ESB_TICK(t_force)
-            n_listed += (unsigned int)S.misc[M_CURLIST];
+            ESB_TICK(L_TFORCE)
+            if (tid == 0) { L[L_EVALS]++; L[L_LISTED] += (unsigned int)S.misc[M_CURLIST]; }
             // post_force of this evaluation, final integrate of the step it closes (it > 0) and initial
             // integrate of the next one (it < n_steps).  __syncthreads_or only tells whether ANY thread
             // passed non-zero, so it carries the rebuild vote; failure bits travel through shared memory.
@@ -1460,11 +1461,11 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             if (rebuild && !S.misc[M_FAIL] && it < d.n_steps) publish_velocities<NP>(a);   // the build's barriers come before the next per-atom phase
 #endif
             rs.eval++;
-            ESB_TICK(t_atom)
+            ESB_TICK(L_TATOM)
             failed = S.misc[M_FAIL];
             if (failed || it == d.n_steps) break;
             rs.step++;
-            n_steps_done++;
+            if (tid == 0) L[L_STEPS]++;
             if (d.adapt_soft) rs.soft_a = ramp(a.ramp_soft[0], a.ramp_soft[1], rs.step, rb, re);
             if (rs.step % 10 == 0) {
                 if (d.adapt_bond1) rs.r0[1] = ramp(a.ramp_bond[1][0], a.ramp_bond[1][1], rs.step, rb, re);
@@ -1482,13 +1483,13 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         if (last_seg && !failed && d.observe && a.act.count > 0) actin_events<NP>(a, r, d, rs, c);
         if (last_seg && !failed && d.microscopy > 0 && a.mic_out && d.microscopy <= a.mic_frames) voxel_counts<NP>(a, r, d.microscopy - 1);
         }
-        ESB_TICK(t_obs)
+        ESB_TICK(L_TOBS)
         __syncthreads();
         failed |= S.misc[M_FAIL];
 #if ESB_CLUSTER
         if (tid == 0) {                                                       // pair statistics: every CTA saw its own quads
             unsigned long long *cn = a.counters + (size_t)r * ESB_N_COUNTERS;
-            atomicAdd(&cn[2], n_pairs); atomicAdd(&cn[3], n_listed);
+            atomicAdd(&cn[2], n_pairs); atomicAdd(&cn[3], (unsigned long long)L[L_LISTED]);
         }
         if (crk != 0) continue;
 #endif
@@ -1506,16 +1507,16 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             rs.status |= failed;
             a.rs[r] = rs;
             unsigned long long *cn = a.counters + (size_t)r * ESB_N_COUNTERS;
-            cn[6] += (unsigned long long)t_atom; cn[7] += (unsigned long long)t_build;
-            cn[8] += (unsigned long long)t_force; cn[9] += (unsigned long long)t_obs;
-            cn[0] += n_evals; cn[1] += n_builds;
+            cn[6] += (unsigned long long)L[L_TATOM]; cn[7] += (unsigned long long)L[L_TBUILD];
+            cn[8] += (unsigned long long)L[L_TFORCE]; cn[9] += (unsigned long long)L[L_TOBS];
+            cn[0] += (unsigned long long)L[L_EVALS]; cn[1] += (unsigned long long)L[L_BUILDS];
 #if !ESB_CLUSTER
             cn[2] += n_pairs;
-            cn[3] += n_listed;
+            cn[3] += (unsigned long long)L[L_LISTED];
 #endif
-            cn[4] += n_steps_done;
+            cn[4] += (unsigned long long)L[L_STEPS];
             cn[5] = (unsigned long long)rs.total_active;
-            cn[10] += n_danger;
+            cn[10] += (unsigned long long)L[L_DANGER];
         }
         __syncthreads();                         // every thread's state stores are issued ...
         if (tid == 0) { __threadfence(); atomicExch(&progress[r], seq + 1); }  // ... and published
