@@ -1340,6 +1340,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
     for (int k = tid; k < a.n_tables * (int)(sizeof(DevTab) / 4); k += ESB_THREADS)
         reinterpret_cast<int *>(S.tab)[k] = reinterpret_cast<const int *>(a.tabs)[k];
     __shared__ int s_item;
+    __shared__ esb_chunk_desc s_desc;
     // A chunk can be cut into n_seg consecutive segments, each its own work item (same arithmetic, finer scheduling
     // grain: a launch of few chunks over more replicas than CTA slots then packs the SMs better).
     const int n_items = a.n_replicas * n_chunks * n_seg;
@@ -1399,7 +1400,13 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         if (tid == 0) { for (int k = L_EVALS; k < L_TMARK; k++) L[k] = 0; L[L_TMARK] = clock64(); }
 #define ESB_TICK(acc) { if (tid == 0) { const long long now_ = clock64(); L[acc] += now_ - L[L_TMARK]; L[L_TMARK] = now_; } }
         int failed = 0;
-        const esb_chunk_desc d = a.descs[c];
+        {   // the chunk descriptor: one copy per CTA in shared memory (a private copy would sit in L2-backed local memory)
+            const int *src = reinterpret_cast<const int *>(&a.descs[c]);
+            int *dst = reinterpret_cast<int *>(&s_desc);
+            for (int k = tid; k < (int)(sizeof(esb_chunk_desc) / 4); k += ESB_THREADS) dst[k] = src[k];
+        }
+        __syncthreads();
+        const esb_chunk_desc &d = s_desc;
         {
             const int *src = reinterpret_cast<const int *>(a.setups + (d.pair_mode == 1 ? 0 : 1 + d.map_id));
             int *dst = reinterpret_cast<int *>(S.setup);
