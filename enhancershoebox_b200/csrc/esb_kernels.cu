@@ -1414,13 +1414,17 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         }
         // ---- Verlet::setup: fix adapt, neighbour build, one force evaluation; then n_steps x
         //      { nve initial; fix adapt; [build]; forces; post_force; nve final } ----
-        const long long first = rs.step - it0, last = first + d.n_steps;     // (it0 steps of this run are done already)
+        // the scalars the step loop advances, as plain values (rs itself is addressable, i.e. in local memory)
+        long long step = rs.step;
+        unsigned long long eval = rs.eval;
+        double soft_a = rs.soft_a, r0_1 = rs.r0[1], r0_2 = rs.r0[2];
+        const long long first = step - it0, last = first + d.n_steps;        // (it0 steps of this run are done already)
         const long long rb = d.ramp_on ? d.ramp_start : first;
         const long long re = d.ramp_on ? d.ramp_stop : last;
         if (!SEG || it0 == 0) {
-            if (d.adapt_soft) rs.soft_a = ramp(a.ramp_soft[0], a.ramp_soft[1], rs.step, rb, re);
-            if (d.adapt_bond1) rs.r0[1] = ramp(a.ramp_bond[1][0], a.ramp_bond[1][1], rs.step, rb, re);
-            if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
+            if (d.adapt_soft) soft_a = ramp(a.ramp_soft[0], a.ramp_soft[1], step, rb, re);
+            if (d.adapt_bond1) r0_1 = ramp(a.ramp_bond[1][0], a.ramp_bond[1][1], step, rb, re);
+            if (d.adapt_bond2) r0_2 = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], step, rb, re);
         } else {
             for (int k = tid; k < a.n_atoms; k += ESB_THREADS) {             // positions at the last build: the rebuild vote goes on
                 const float4 b = __ldcg(&a.bref4[(size_t)r * np + k]);
@@ -1437,8 +1441,8 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         const bool last_seg = SEG ? it1 == d.n_steps + 1 : true;
         for (int it = it0; it < it1; it++) {
             if (rebuild) { build_lists<NP, P16>(a, r); if (tid == 0) { L[L_BUILDS]++; if (ago == delay) L[L_DANGER]++; } ago = 0; ESB_TICK(L_TBUILD) }
-            if (d.pair_mode == 1) force_phase<NP, 1, false, P16>(a, r, (float)rs.soft_a, (float)rs.r0[1], (float)rs.r0[2], nullptr);
-            else force_phase<NP, 2, false, P16>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], nullptr);
+            if (d.pair_mode == 1) force_phase<NP, 1, false, P16>(a, r, (float)soft_a, (float)r0_1, (float)r0_2, nullptr);
+            else force_phase<NP, 2, false, P16>(a, r, 0.0f, (float)r0_1, (float)r0_2, nullptr);
             __syncthreads();
             if (tid == 0) S.misc[M_QCTR] = 0;                        // (visible to the next force loop through the per-atom phase's barrier)
             ESB_TICK(L_TFORCE)
@@ -1446,7 +1450,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             // post_force of this evaluation, final integrate of the step it closes (it > 0) and initial
             // integrate of the next one (it < n_steps).  __syncthreads_or only tells whether ANY thread
             // passed non-zero, so it carries the rebuild vote; failure bits travel through shared memory.
-            rebuild = __syncthreads_or(atom_phase<NP>(a, it > 0, it < d.n_steps, k0, k1, rs.eval));
+            rebuild = __syncthreads_or(atom_phase<NP>(a, it > 0, it < d.n_steps, k0, k1, eval));
 #if ESB_CLUSTER
             {   // ONE cluster barrier per step: the next positions went into the other buffer of every CTA, votes and
                 // failure bits into slots of this step's parity (a CTA is never more than one barrier ahead)
@@ -1467,16 +1471,16 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
 #if ESB_CLUSTER
             if (rebuild && !S.misc[M_FAIL] && it < d.n_steps) publish_velocities<NP>(a);   // the build's barriers come before the next per-atom phase
 #endif
-            rs.eval++;
+            eval++;
             ESB_TICK(L_TATOM)
             failed = S.misc[M_FAIL];
             if (failed || it == d.n_steps) break;
-            rs.step++;
+            step++;
             if (tid == 0) L[L_STEPS]++;
-            if (d.adapt_soft) rs.soft_a = ramp(a.ramp_soft[0], a.ramp_soft[1], rs.step, rb, re);
-            if (rs.step % 10 == 0) {
-                if (d.adapt_bond1) rs.r0[1] = ramp(a.ramp_bond[1][0], a.ramp_bond[1][1], rs.step, rb, re);
-                if (d.adapt_bond2) rs.r0[2] = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], rs.step, rb, re);
+            if (d.adapt_soft) soft_a = ramp(a.ramp_soft[0], a.ramp_soft[1], step, rb, re);
+            if (step % 10 == 0) {
+                if (d.adapt_bond1) r0_1 = ramp(a.ramp_bond[1][0], a.ramp_bond[1][1], step, rb, re);
+                if (d.adapt_bond2) r0_2 = ramp(a.ramp_bond[2][0], a.ramp_bond[2][1], step, rb, re);
             }
         }
         const unsigned long long n_pairs = (unsigned int)S.misc[M_PAIRS];
@@ -1484,6 +1488,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
         publish_velocities<NP>(a);
         csync();                                                             // rank 0 stores the state: it needs every bead's velocity
 #endif
+        rs.step = step; rs.eval = eval; rs.soft_a = soft_a; rs.r0[1] = r0_1; rs.r0[2] = r0_2;
         if (SEG) { rs.ago = ago; rs.rebuild = rebuild; rs.curlist = S.misc[M_CURLIST]; }
         if (crk == 0) {                                                      // (cluster variant: every CTA holds the same state; one of them reports)
         if (last_seg && !failed && d.observe) observe<NP>(a, r, d, rs, delt, sig_nm, c);
