@@ -27,6 +27,9 @@
 #define ESB_NL_STRIDE 2048           // bead owns an arena of this many entries: a system of up to 2048 beads cannot
 #endif
                                      // overflow it (LAMMPS: neigh_modify one 10000 page 100000, run_single_shoebox.py:533)
+#ifndef ESB_BUILD_REVERSE
+#define ESB_BUILD_REVERSE 1
+#endif
 #define ESB_NCLASS 6                 // species classes for the row sort: chromatin-like, actin, RBP, RNP, Ser5P, gene body (induced/active)
 #define ESB_N_COUNTERS 11             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases, dangerous builds
 #define ESB_ACT_WORDS(count) (2 + 3 * (count))

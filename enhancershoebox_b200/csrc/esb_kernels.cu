@@ -325,6 +325,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         if (lane == 0) q = atomicAdd(&S.misc[M_QCTR], 1);
         q = __shfl_sync(FULL, q, 0) * csize() + crank();         // (cluster variant: the quads are dealt to the CTAs of the cluster)
         if (q >= nquads) break;
+        if (ESB_BUILD_REVERSE) q = nquads - 1 - q;               // last classes of the quad order first (gene body, Ser5P, RNP: the long scans)
         int ia[4], ta[4], cnt[4];
         float4 pa[4];
         float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f, zmin = 3.0e38f, zmax = -3.0e38f;
