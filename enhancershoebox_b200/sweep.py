@@ -57,6 +57,8 @@ def gather_rows(local: np.ndarray, n_total: int, group=None, device=None) -> np.
     width = max(counts)
     t = torch.zeros((width,) + tuple(local.shape[1:]), dtype=torch.float64)
     t[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
+    if device is None and "nccl" in str(dist.get_backend(group)):
+        device = torch.device("cuda", torch.cuda.current_device())      # NCCL moves device tensors only
     if device is not None:
         t = t.to(device)
     parts = [torch.empty_like(t) for _ in range(world)]
@@ -127,7 +129,11 @@ def run_sweep(box: int, promoters=(1, 2, 3), activations=(30,), thresholds=(10, 
                     pending.append(g)
             if progress:
                 progress(rank, p, len(now), len(pending))
-    return groups, gather_rows(rows, len(groups))
+    gather_dev = None
+    if dist.is_available() and dist.is_initialized() and "nccl" in str(dist.get_backend()):
+        import torch
+        gather_dev = torch.device("cuda", device)
+    return groups, gather_rows(rows, len(groups), device=gather_dev)
 
 
 def summary_csv(groups, rows) -> str:

@@ -2,6 +2,7 @@
 (box 11, promoter 3, threshold 20, activation 100/1000) over N replicas x 400 chunks.
 Run here (CPU): python tests/golden/make_oracle_ensemble.py <first_replica> <n_replicas> <out.npz>
 then merge with --merge.  Used by tests/test_gpu_ensemble.py as the statistical reference.
+ESB_ENSEMBLE_CHUNKS=2000 makes the full-length fixture oracle_ensemble_box11_2000.npz (production run length, 90 % RNP).
 (Regenerated with the oracle's `neigh_modify delay 10` rule: 8 x `make_oracle_ensemble.py 6k 6 part_k.npz`, then
 `--merge oracle_ensemble_box11.npz part_*.npz`.)"""
 import sys, os, time
@@ -10,7 +11,7 @@ import numpy as np
 from enhancershoebox_b200 import datafile, ljsoft, protocol as P
 from oracle import esb_oracle as O, observe as OB
 
-NCH, THR, ACT = 400, 20, 100
+NCH, THR, ACT = int(os.environ.get('ESB_ENSEMBLE_CHUNKS', '400')), 20, 100
 
 def run(first, count, out):
     pt = P.pair_tables('genes_stages')

@@ -1,0 +1,46 @@
+"""Level 3 parity against the reference-held ensemble tables (VisitorGeneMaps/
+summary_contact_all_Thresholds10-100.txt is the statistical oracle; BASELINE.md quotes five cells).
+
+The device runs the PRODUCTION protocol -- box 11, fresh make_input_file initial conditions, soft phase, table
+switch, 2000 Python timesteps x 200 MD steps, gene state machine, RBP->RNP ramp to 90 % -- 100 repeats per cell for
+the five quoted cells and compares S5PInt, S2PInt, Contact, DistActivation (mean over repeats; DistActivation over the
+activating repeats) and the fraction of activating repeats with the 100 LAMMPS repeats of the same cell.
+Stated tolerance: |z| < 4 per comparison (both samples' standard errors), sum of z^2 over the 25 comparisons < 60
+(chi^2_25: p = 1e-4), S2PInt a whole number of frames out of 1850."""
+import numpy as np
+import pytest
+
+import ensemble_compare as EC
+from enhancershoebox_b200 import datafile, engine as E
+
+pytestmark = pytest.mark.gpu
+QUOTED = [(3, 80, 30), (1, 80, 30), (2, 50, 10), (3, 10, 100), (3, 100, 1)]
+REPEATS = 100
+
+
+def test_production_ensembles_match_the_reference_tables():
+    cells, _ = EC.load_golden()
+    zs, report = [], {}
+    for p in (1, 2, 3):
+        runs = [(c, k) for c in QUOTED if c[0] == p for k in range(REPEATS)]
+        seeds = np.array([31_000_000 + 1000 * (c[1] * 1000 + c[2]) + k for c, k in runs], dtype=np.uint64)
+        datas = [datafile.make_shoebox(11, p, False, seed=int(s)) for s in seeds]
+        eng = E.ShoeboxBatch(datas, seeds=seeds, thresholds=[c[1] for c, _ in runs], activations=[c[2] for c, _ in runs])
+        eng.set_schedule(2000, observe=True)
+        eng.run()
+        ok = eng.status() == 0
+        assert ok.mean() > 0.97                       # LAMMPS loses a run now and then too (the launcher retries)
+        rows = E.aggregate_all(eng.frames())
+        eng.close()
+        for c in QUOTED:
+            if c[0] != p:
+                continue
+            sel = np.array([cc == c for cc, _ in runs]) & ok
+            comp = EC.compare_cell(rows[sel], cells[c])
+            report[",".join(map(str, c))] = comp
+            assert EC.s2p_is_quantised(rows[sel])
+            zs += [q[-1] for q in comp]
+    print(EC.table(report))
+    zs = np.array(zs)
+    assert np.all(np.abs(zs) < 4.0), EC.table(report)
+    assert float((zs ** 2).sum()) < 60.0, EC.table(report)

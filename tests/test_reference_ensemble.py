@@ -1,0 +1,37 @@
+"""The committed device ensembles (profiles/r2_reference_ensemble_*.json, written on a B200 by
+scripts/reference_ensemble.py) against the reference's own LAMMPS sweep -- the same comparison as
+tests/test_gpu_reference_ensemble.py, re-checkable without a GPU -- and the known answers of the golden table."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import ensemble_compare as EC
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_golden_table_known_answers():
+    cells, rows = EC.load_golden()
+    assert len(cells) == 330 and all(c["n"] == 100 for c in cells.values())
+    c = cells[(3, 80, 30)]                                  # 17.28 +- 19.80, 6.67 +- 9.97, 7.19 +- 10.86, 123.2 +- 19.5 (44)
+    assert abs(c["s5p"][0] - 17.28) < 0.01 and abs(c["s2p"][0] - 6.67) < 0.01 and abs(c["contact"][0] - 7.19) < 0.01
+    assert c["n_act"] == 44 and abs(c["dist"][0] - 123.2) < 0.1
+    for r in rows.values():                                 # the S2PInt quantum of the reference's own runs
+        q = r[:, 1] / EC.S2P_QUANTUM
+        assert np.allclose(q, np.round(q), atol=1e-6)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_reference_ensemble_*.json"))))
+def test_committed_device_ensembles_match_the_reference(path):
+    comp, res = EC.compare_result_file(path)
+    assert res["chunks"] == 2000 and res["box"] == 11
+    n_runs = sum(len(v) for v in res["cells"].values())
+    assert res["failed"] <= 0.03 * (n_runs + res["failed"])
+    zs = np.array([q[-1] for c in comp.values() for q in c if np.isfinite(q[-1])])
+    # per comparison |z| < 4 when the cell has the reference's 100 repeats; sweeps with fewer repeats per cell are
+    # judged on the distribution of z over all cells: mean ~ 0, rms ~ 1
+    assert np.all(np.abs(zs) < 4.5), EC.table(comp)
+    assert abs(zs.mean()) < 4.0 / np.sqrt(len(zs)) + 0.05 and 0.5 < zs.std() < 1.5, (zs.mean(), zs.std())
