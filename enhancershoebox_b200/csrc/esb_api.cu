@@ -167,13 +167,14 @@ int rebuild_setups(esb_handle *h)
     if (!h->have_box) return fail(ESB_ESTATE, "esb_set_box must be called first");
     // ---- row grid of the list build: rows over (y, z) of edge row_edge, every row spans the box in x.
     //      The build scratch (the 3 force arrays, 12 n_pad bytes) holds the (class, row) table (2 B per slot),
-    //      two u16 index arrays and the sorted x coordinates (4 B per bead): slots + 2 <= 2 n_pad.
-    const int cap = 2 * h->n_pad - 16;
+    //      three u16 index arrays and the sorted x coordinates (4 B per bead): slots + 2 <= n_pad.  The build packs
+    //      a quad's first row and row count in y and z into 8 bits each.
+    const int cap = h->n_pad - 16;
     double c = h->cell_edge;
     for (;;) {
         h->nry = std::max(1, (int)ceil((h->hi[1] - h->lo[1]) / c));
         h->nrz = std::max(1, (int)ceil((h->hi[2] - h->lo[2]) / c));
-        if ((long long)h->nry * h->nrz * ESB_NCLASS <= cap) break;
+        if ((long long)h->nry * h->nrz * ESB_NCLASS <= cap && h->nry <= 255 && h->nrz <= 255) break;
         c *= 1.05;
     }
     h->cell_edge = c;

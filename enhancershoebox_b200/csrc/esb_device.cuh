@@ -31,7 +31,7 @@
 #define ESB_BUILD_REVERSE 1
 #endif
 #define ESB_NCLASS 6                 // species classes for the row sort: chromatin-like, actin, RBP, RNP, Ser5P, gene body (induced/active)
-#define ESB_N_COUNTERS 11             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases, dangerous builds
+#define ESB_N_COUNTERS 12             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases, dangerous builds, max |pair force| * 256
 #define ESB_ACT_WORDS(count) (2 + 3 * (count))
 #define ESB_NOLINK 0xffffu
 #define ESB_N_SETUPS 9               // 0 = pair soft, 1..4 = table maps 0..3 (closed form + patch), 5..8 = same maps, array lookups

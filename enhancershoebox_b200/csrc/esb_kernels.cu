@@ -57,13 +57,14 @@ struct Smem {
     unsigned short *cend;        // [nslots + 2]  running end offset of every slot
     unsigned short *sidx;        // [n_pad]       atom indices sorted by (slot, x); a second [n_pad] block behind it is sort scratch
     float *xs;                   // [n_pad]       x of the sorted beads
+    unsigned short *spos;        // [n_pad]       position of every bead in the sorted (candidate) order
     unsigned short *qord;        // [n_pad]       quad order of the build (own region: it outlives the scratch reuse)
     unsigned char *owner;        // [n_pad]       cluster variant: rank of the CTA that owns the bead (its force quad)
     float4 *pos_next;            // cluster variant: the other position buffer (written by the per-atom phase of all CTAs)
     unsigned short *mine;        // cluster variant: the beads this CTA owns (any order), misc[M_NMINE] of them
 };
 
-enum { M_QCTR = 0 /* next quad of the running build / force loop */, M_FAIL, M_PAIRS, M_CURLIST, M_SCAN /* one per warp */,
+enum { M_QCTR = 0 /* next quad of the running build / force loop */, M_FAIL, M_PAIRS, M_CURLIST, M_FMAX /* largest |pair force| of the chunk, 2^-8 units */, M_SCAN /* one per warp */,
        M_CNT_PROM = M_SCAN + ESB_THREADS / 32, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */,
 #if ESB_CLUSTER
        M_PARITY = M_HIST + 52 /* which of the two position buffers is current */, M_NMINE /* beads this CTA owns */, M_VOTE /* rebuild vote [parity][rank] */,
@@ -139,6 +140,7 @@ __device__ __forceinline__ Smem carve(const KArgs &a, const bool first_buffer = 
     S.cend = reinterpret_cast<unsigned short *>(S.fx);
     S.sidx = S.cend + ((a.nrows * ESB_NCLASS + 2 + 7) & ~7);
     S.xs = reinterpret_cast<float *>(S.sidx + 2 * np);
+    S.spos = reinterpret_cast<unsigned short *>(S.xs + np);
     return S;
 }
 
@@ -166,6 +168,40 @@ __device__ __forceinline__ float4 lds128(const unsigned int addr)
     float4 v;
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
+}
+// Pair forces are accumulated as 32-bit fixed-point integers (ESB_FSCALE counts per force unit): integer addition is
+// associative, so a bead's force does not depend on the order in which its pairs are visited, and shared-memory integer
+// atomics are native (ATOMS.ADD, ~3 cycles per warp instruction at random addresses -- profiles/r2_microbench_smem.log --
+// whereas fp32 shared atomics are CAS loops on sm_100).  That is what makes Newton's third law affordable here: the
+// HALF list (every unordered pair stored once) evaluates a pair once, keeps bead i's share in registers and scatters
+// -f to bead j.  Scale 2^16: resolution 1.5e-5 (a bead's ~60 roundings add up to ~3e-5 rms on forces of order 10..100,
+// 1e-6 of the Langevin noise amplitude), range +-32768.  Measured headroom (scripts/force_headroom.py, 296 box-11 runs x
+// 400 chunks, profiles/r2_force_headroom.log): the largest pair-force component of a chunk is typically 150..350 and
+// reached 1923 once (a bead whose type -- hence core size -- had just changed inside the Ser5P cluster); one LJsoft
+// pair contributes at most ~365.  A bead whose sum leaves half the range (16384) flags the replica (ESB_ST_NONFINITE)
+// in the per-atom phase; counter 11 reports the largest sum seen.
+#define ESB_FSCALE 0x1p16f
+#ifndef ESB_FGUARD
+#define ESB_FGUARD 1
+#endif
+#ifndef ESB_HALF
+#define ESB_HALF (!ESB_CLUSTER)      // the cluster variant deals the quads to several CTAs and keeps the full list (no remote scatter)
+#endif
+template <int NP>
+__device__ __forceinline__ unsigned int force_off(const KArgs &a) { return 28u * (unsigned int)(NP ? NP : a.n_pad); }   // byte offset of S.fx
+// f[j] += (vx, vy, vz) for the three SoA force arrays; addr = shared address of fx[j]
+template <int NP>
+__device__ __forceinline__ void red_add3(const KArgs &a, const unsigned int addr, const int vx, const int vy, const int vz)
+{
+    if (NP) {
+        asm volatile("red.shared.add.s32 [%0], %1;\n\tred.shared.add.s32 [%0+%4], %2;\n\tred.shared.add.s32 [%0+%5], %3;"
+                     :: "r"(addr), "r"(vx), "r"(vy), "r"(vz), "n"(4 * NP), "n"(8 * NP) : "memory");
+    } else {
+        const unsigned int st = 4u * (unsigned int)a.n_pad;
+        asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr), "r"(vx) : "memory");
+        asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr + st), "r"(vy) : "memory");
+        asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr + 2u * st), "r"(vz) : "memory");
+    }
 }
 template <int NP>
 __device__ __forceinline__ int tab_off4(const KArgs &a)
@@ -242,7 +278,7 @@ __device__ __forceinline__ void slot_sort(const Smem &S, const KArgs &a, const i
 // j->i) so the force loop needs no scatter; every entry carries the pair's table id.
 //
 // Beads are counting-sorted into slots = (species class, row), a row being a (y, z) column of edge
-// ~1.2 that spans the box in x, and ordered by x inside a slot.  The candidates of a bead towards
+// 2.8 that spans the box in x, and ordered by x inside a slot.  The candidates of a bead towards
 // class B are then, for every row within reach(type, B) in y and z, ONE contiguous span of the sorted
 // order: the beads of that row with x within reach -- found by binary search, at full resolution in x
 // and with the cutoff of that class pair (0.7 for RBP-RBP ... 3.2 for RNP-RNP) instead of the
@@ -302,6 +338,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
             }
             S.sidx[s0 + rank] = (unsigned short)i;
             S.xs[s0 + rank] = p.x;
+            S.spos[i] = (unsigned short)(s0 + rank);
         }
         __syncthreads();
     }
@@ -327,9 +364,11 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         if (q >= nquads) break;
         if (ESB_BUILD_REVERSE) q = nquads - 1 - q;               // last classes of the quad order first (gene body, Ser5P, RNP: the long scans)
         int ia[4], ta[4], cnt[4];
+        int sp_[4];                                              // HALF: position of the bead in the candidate order
         float4 pa[4];
         float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f, zmin = 3.0e38f, zmax = -3.0e38f;
         bool any_topo = false;
+        int cls_min = ESB_NCLASS, spos_min = 0x7fffffff;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int idx = min(4 * q + b, n - 1);               // the last quad may repeat its last bead
@@ -341,7 +380,16 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
             ymin = fminf(ymin, pa[b].y); ymax = fmaxf(ymax, pa[b].y);
             zmin = fminf(zmin, pa[b].z); zmax = fmaxf(zmax, pa[b].z);
             any_topo |= ia[b] < n_topo;
+            if (ESB_HALF) {
+                sp_[b] = S.spos[ia[b]];
+                spos_min = min(spos_min, sp_[b]);
+                cls_min = min(cls_min, (int)a.class_of[ta[b]]);
+            } else sp_[b] = 0;
         }
+        // HALF list: bead i lists candidate j only when j comes AFTER i in the candidate order (class, row, x), so every
+        // unordered pair is stored -- and evaluated -- once.  Classes before the quad's lowest class hold no such
+        // candidate, and in that class the rows before the quad's first z row hold none either.
+        const int zrow_min = ESB_HALF ? cell_coord(zmin, a.lo[2], a.row_inv, a.nrz) : 0;
         // spans of the quad: for class B every row within reach of the quad's bounding box; the span list is the
         // concatenation over the classes.  Lane B < ESB_NCLASS works out and keeps the numbers of class B:
         // my_pack = first y row | rows in y << 8 | first z row << 16, spans [my_cum, my_end), reach.
@@ -354,9 +402,11 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
                 const float c = fmaxf(fmaxf(rc[ta[0] * 8], rc[ta[1] * 8]), fmaxf(rc[ta[2] * 8], rc[ta[3] * 8]));
                 const int first = lane * nrows;
                 const int pop = (int)S.cend[first + nrows - 1] - (first ? (int)S.cend[first - 1] : 0);
-                if (c > 0.0f && pop > 0) {
+                if (c > 0.0f && pop > 0 && (!ESB_HALF || lane >= cls_min)) {
                     const int y0 = cell_coord(ymin - c, loy, rinv, nry), y1 = cell_coord(ymax + c, loy, rinv, nry);
-                    const int z0 = cell_coord(zmin - c, loz, rinv, nrz), z1 = cell_coord(zmax + c, loz, rinv, nrz);
+                    int z0 = cell_coord(zmin - c, loz, rinv, nrz);
+                    const int z1 = cell_coord(zmax + c, loz, rinv, nrz);
+                    if (ESB_HALF && lane == cls_min) z0 = max(z0, zrow_min);
                     my_pack = y0 | ((y1 - y0 + 1) << 8) | (z0 << 16);
                     my_reach = c;
                     nsp = (y1 - y0 + 1) * (z1 - z0 + 1);
@@ -397,6 +447,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
                 const float xlo = xmin - reach, xhi = xmax + reach;
                 int ka = 0, kb = 0;
                 if (slot >= 0) { ka = slot ? (int)S.cend[slot - 1] : 0; kb = (int)S.cend[slot]; }
+                if (ESB_HALF) ka = min(max(ka, spos_min + 1), kb);   // nothing at or before the quad's first bead can be listed
                 {   // first bead with x >= xlo, then first bead with x > xhi
                     int lo_ = ka, hi_ = kb;
                     while (__any_sync(FULL, lo_ < hi_)) {
@@ -443,7 +494,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
                         const float dx = pa[b].x - pj.x, dy = pa[b].y - pj.y, dz = pa[b].z - pj.z;
                         const float r2 = dx * dx + dy * dy + dz * dz;
                         const float cs = UNIFORM ? cs_u : cs_row[ta[b] * ESB_MAXT + tj];
-                        bool ok = live && (r2 < cs) && (j != ia[b]);
+                        bool ok = live && (r2 < cs) && (ESB_HALF ? (k > sp_[b]) : (j != ia[b]));
                         if (TOPO) {
                             if (ok && j < n_topo && ia[b] < n_topo) {
                                 const uint4 sp4 = __ldcg(reinterpret_cast<const uint4 *>(a.spec + (size_t)r * a.spec_stride + (size_t)ia[b] * ESB_MAX_SPEC));
@@ -477,7 +528,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
             if (idx < n) {
                 if (c > ESB_NL_MAXNB) { atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH); c = ESB_NL_MAXNB; }
                 qbuild[idx] = make_uint2((unsigned int)i * ESTRIDE, (unsigned int)i | ((unsigned int)c << 16));
-                listed += c;
+                listed += ESB_HALF ? 2 * c : c;                  // the counters report ordered pairs
             }
         }
     }
@@ -490,12 +541,12 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
     // ---- force order: descriptors sorted by decreasing list length (counting sort on the length) ----
     if (crank() == 0) {
         uint2 *qforce = a.nl_qinfo + (size_t)r * 2 * a.n_pad;
-        int *hist = reinterpret_cast<int *>(S.fx);                 // 1024 counters; the scratch is free again
+        int *hist = reinterpret_cast<int *>(S.fx);                 // 2048 counters; the scratch is free again
         for (int k = tid; k < ESB_NL_MAXNB + 1; k += ESB_THREADS) hist[k] = 0;
         __syncthreads();
         for (int k = tid; k < n; k += ESB_THREADS) atomicAdd(&hist[ESB_NL_MAXNB - (int)(__ldcg(&qbuild[k]).y >> 16)], 1);
         __syncthreads();
-        // exclusive scan of the 1024 counters: an equal share per thread
+        // exclusive scan of the 2048 counters: an equal share per thread
         constexpr int PER = (ESB_NL_MAXNB + ESB_THREADS) / ESB_THREADS;
         int v[PER], s = 0;
 #pragma unroll
@@ -528,6 +579,11 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
 #endif
     if (tid == 0) S.misc[M_QCTR] = 0;                            // the force loop hands out quads from 0
     __syncthreads();   // lists (global) and the scratch alias are settled before forces are written
+    {   // the scratch becomes the (integer) pair-force accumulators again: they are added to, so they start at zero
+        int *fi = reinterpret_cast<int *>(S.fx);
+        for (int k = tid; k < 3 * a.n_pad; k += ESB_THREADS) fi[k] = 0;
+    }
+    __syncthreads();
 #if ESB_CLUSTER
     __threadfence();
     csync();                                                     // force order (global) and owners (every CTA) are in place
@@ -646,11 +702,14 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
 #if ESB_CLUSTER
     const unsigned int sb0 = smem_base(), tbase = sb0 + 16u * (unsigned int)tab_off4<NP>(a);
     const unsigned int sb = sb0 + (unsigned int)(reinterpret_cast<unsigned char *>(S.pos) - smem_raw);      // current position buffer
+    const unsigned int sb0_ = sb0;
 #else
     const unsigned int sb = smem_base(), tbase = sb + 16u * (unsigned int)tab_off4<NP>(a);
+    const unsigned int sb0_ = sb;
 #endif
     const float *tabval = a.tabval;
     const int tlm1 = a.tlm1;
+    const unsigned int fbase = sb0_ + force_off<NP>(a);          // shared address of the force accumulators
     unsigned int npairs = 0;
     // quads in order of decreasing list length, handed out dynamically (longest first: the warps finish
     // together); the next quad's descriptor is fetched (L2) while the current one is processed
@@ -673,7 +732,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
         const unsigned int *nl = pool + qi.x;
         const float4 pi = lds128(sb + 16u * (unsigned int)i);
         const int cnt_max = __reduce_max_sync(FULL, cnt);
-        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        int fx = 0, fy = 0, fz = 0;                               // fixed point, ESB_FSCALE_* counts per force unit
         // The list lives in L2/HBM: ESB_PREFETCH loads per lane are kept in flight (entries e, e+G, ...)
         // so that their latency overlaps the arithmetic of the entries before them.
         // Loads past the end of a list are harmless (every bead owns a fixed arena and the pool is padded),
@@ -693,8 +752,8 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                     const float rr = sqrtf(r2);
                     const float xr = rr * irc;                               // r / rc in [0, 1)
                     fpair = (rr > 0.0f) ? soft_a * sinpif(xr) * 3.14159265358979323846f * irc / rr : 0.0f;
-                    if (ENERGY) e_pair += 0.5 * (double)(soft_a * (1.0f + cospif(xr)));
-                    npairs++;
+                    if (ENERGY) e_pair += (ESB_HALF ? 1.0 : 0.5) * (double)(soft_a * (1.0f + cospif(xr)));
+                    npairs += ESB_HALF ? 2 : 1;
                 } else {
                     const unsigned int tb = P16 ? (ent >> 11) & 0x1fu : ent >> 16;   // table id of the pair (fixed between builds)
                     const unsigned int T4 = tbase + 48u * tb;                         // DevTab = 3 float4 words
@@ -725,10 +784,15 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                     const float inv = rcp_approx(x);                                // <= 1 ulp: 3 ulp on inv^3, far inside the 1e-5 parity bound
                     fpair = t1.x * q2 * (2.0f - x) * (inv * inv * inv);
                     if (!closed) fpair = tabval[tb * (unsigned int)tlm1 + it];   // predicated load: patch bins are rare
-                    if (ENERGY) e_pair += 0.5 * (double)a.tabe[tb * (unsigned int)tlm1 + it];
-                    npairs++;
+                    if (ENERGY) e_pair += (ESB_HALF ? 1.0 : 0.5) * (double)a.tabe[tb * (unsigned int)tlm1 + it];
+                    npairs += ESB_HALF ? 2 : 1;
                 }
-                fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+                // round(f * scale) is odd in f, so bead j's share is exactly the negative of bead i's: the sums are the
+                // same integers whether a pair is visited once (half list + scatter) or from both sides (full list)
+                const float fs = fpair * ESB_FSCALE;
+                const int ix = __float2int_rn(dx * fs), iy = __float2int_rn(dy * fs), iz = __float2int_rn(dz * fs);
+                fx += ix; fy += iy; fz += iz;
+                if (ESB_HALF) red_add3<NP>(a, fbase + 4u * (ent & (P16 ? 0x7ffu : 0xffffu)), -ix, -iy, -iz);
             }
         };
         constexpr int DEPTH = ESB_PREFETCH;                       // list words in flight per lane
@@ -765,7 +829,10 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
             fy += __shfl_xor_sync(FULL, fy, d);
             fz += __shfl_xor_sync(FULL, fz, d);
         }
-        if (valid && gl == 0) { S.fx[i] = fx; S.fy[i] = fy; S.fz[i] = fz; }
+        if (valid && gl == 0) {
+            if (ESB_HALF) red_add3<NP>(a, fbase + 4u * (unsigned int)i, fx, fy, fz);      // other beads' lists scatter into this one too
+            else { S.fx[i] = __int_as_float(fx); S.fy[i] = __int_as_float(fy); S.fz[i] = __int_as_float(fz); }
+        }
         q = qn; qi = qi_next;
     }
     if (npairs) atomicAdd(&S.misc[M_PAIRS], (int)npairs);
@@ -826,12 +893,13 @@ __device__ __forceinline__ int post_force(const KArgs &a, int i, const float4 p,
 // ------------------------------------------------------------------------------------------------
 template <int NP>
 __device__ __noinline__ int atom_phase(const KArgs &a, const bool do_final, const bool do_initial,
-                                       const uint32_t k0, const uint32_t k1, const unsigned long long eval)
+                                       const uint32_t k0, const uint32_t k1, const unsigned long long eval, const float inv_fscale)
 {
     const Smem S = carve<NP>(a);
     int flags = 0;
     const float dtf = 0.5f * a.dt, dtv = a.dt;
     double dummy = 0.0;
+    unsigned int fmax_seen = 0u;
 #if ESB_CLUSTER
     for (int k = threadIdx.x; k < S.misc[M_NMINE]; k += ESB_THREADS) {   // integrated by its owner, which writes it into every CTA
         const int i = S.mine[k];
@@ -841,8 +909,15 @@ __device__ __noinline__ int atom_phase(const KArgs &a, const bool do_final, cons
         float4 p = S.pos[i];
         float vx = S.vx[i], vy = S.vy[i], vz = S.vz[i];
         const bool topo = i < a.n_topo;
-        float fx = (topo ? S.gx[i] : 0.0f) + S.fx[i], fy = (topo ? S.gy[i] : 0.0f) + S.fy[i], fz = (topo ? S.gz[i] : 0.0f) + S.fz[i];    // bonded + pair
-        const int fail = post_force<false>(a, i, p, vx, vy, vz, fx, fy, fz, k0, k1, eval, dummy);
+        // bonded + pair (fixed point -> fp32; the accumulators go back to zero for the next evaluation)
+        const int ifx = __float_as_int(S.fx[i]), ify = __float_as_int(S.fy[i]), ifz = __float_as_int(S.fz[i]);
+        if (ESB_HALF) { S.fx[i] = 0.0f; S.fy[i] = 0.0f; S.fz[i] = 0.0f; }
+        float fx = (topo ? S.gx[i] : 0.0f) + (float)ifx * inv_fscale, fy = (topo ? S.gy[i] : 0.0f) + (float)ify * inv_fscale,
+              fz = (topo ? S.gz[i] : 0.0f) + (float)ifz * inv_fscale;
+        int fail = post_force<false>(a, i, p, vx, vy, vz, fx, fy, fz, k0, k1, eval, dummy);
+        const unsigned int iabs = max(max((unsigned int)abs(ifx), (unsigned int)abs(ify)), (unsigned int)abs(ifz));
+        if (ESB_FGUARD && iabs > 0x40000000u) fail |= ESB_ST_NONFINITE;      // the pair force left half the fixed-point range
+        fmax_seen = max(fmax_seen, iabs);
         if (fail) atomicOr(&S.misc[M_FAIL], fail);
         if (do_final) { vx += dtf * fx; vy += dtf * fy; vz += dtf * fz; }
         if (do_initial) {
@@ -859,6 +934,11 @@ __device__ __noinline__ int atom_phase(const KArgs &a, const bool do_final, cons
             for (int rk = 0; rk < csize(); rk++) peer(S.pos_next, rk)[i] = p;    // (nobody reads it during this step)
 #endif
         S.vx[i] = vx; S.vy[i] = vy; S.vz[i] = vz;                // (cluster: only the owner needs the velocity until ownership changes)
+    }
+    {   // headroom diagnostic: largest pair-force component of the chunk in 2^-8 force units (one atomic per warp)
+        fmax_seen = __reduce_max_sync(0xffffffffu, fmax_seen);
+        const int v8 = (int)fminf((float)fmax_seen * inv_fscale * 256.0f, 2.0e9f);
+        if ((threadIdx.x & 31) == 0 && v8 > S.misc[M_FMAX]) atomicMax(&S.misc[M_FMAX], v8);
     }
     return flags;
 }
@@ -1394,6 +1474,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             S.pos[k] = __ldcg(&a.pos4[(size_t)r * np + k]);                 // written by another SM one chunk ago: bypass L1
             const float4 v = __ldcg(&a.vel4[(size_t)r * np + k]);
             S.vx[k] = v.x; S.vy[k] = v.y; S.vz[k] = v.z;
+            S.fx[k] = 0.0f; S.fy[k] = 0.0f; S.fz[k] = 0.0f;       // (a segment that continues a chunk starts without a build)
         }
         for (int k = tid; k < M_END; k += ESB_THREADS) S.misc[k] = (SEG && k == M_CURLIST && it0 > 0) ? rs.curlist : 0;
         const uint32_t k0 = (uint32_t)rs.seed, k1 = (uint32_t)(rs.seed >> 32);
@@ -1451,7 +1532,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             // post_force of this evaluation, final integrate of the step it closes (it > 0) and initial
             // integrate of the next one (it < n_steps).  __syncthreads_or only tells whether ANY thread
             // passed non-zero, so it carries the rebuild vote; failure bits travel through shared memory.
-            rebuild = __syncthreads_or(atom_phase<NP>(a, it > 0, it < d.n_steps, k0, k1, eval));
+            rebuild = __syncthreads_or(atom_phase<NP>(a, it > 0, it < d.n_steps, k0, k1, eval, 1.0f / ESB_FSCALE));
 #if ESB_CLUSTER
             {   // ONE cluster barrier per step: the next positions went into the other buffer of every CTA, votes and
                 // failure bits into slots of this step's parity (a CTA is never more than one barrier ahead)
@@ -1530,6 +1611,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             cn[4] += (unsigned long long)L[L_STEPS];
             cn[5] = (unsigned long long)rs.total_active;
             cn[10] += (unsigned long long)L[L_DANGER];
+            if ((unsigned long long)S.misc[M_FMAX] > cn[11]) cn[11] = (unsigned long long)S.misc[M_FMAX];
         }
         __syncthreads();                         // every thread's state stores are issued ...
         if (tid == 0) { __threadfence(); atomicExch(&progress[r], seq + 1); }  // ... and published
@@ -1577,7 +1659,9 @@ esb_forces_kernel(const __grid_constant__ KArgs a, const int pair_mode, const in
     double e_wall = 0.0;
     for (int i = tid; i < a.n_atoms; i += ESB_THREADS) {
         const bool topo = i < a.n_topo;
-        float fx = (topo ? S.gx[i] : 0.0f) + S.fx[i], fy = (topo ? S.gy[i] : 0.0f) + S.fy[i], fz = (topo ? S.gz[i] : 0.0f) + S.fz[i];
+        const float inv_fscale = 1.0f / ESB_FSCALE;
+        float fx = (topo ? S.gx[i] : 0.0f) + (float)__float_as_int(S.fx[i]) * inv_fscale, fy = (topo ? S.gy[i] : 0.0f) + (float)__float_as_int(S.fy[i]) * inv_fscale,
+              fz = (topo ? S.gz[i] : 0.0f) + (float)__float_as_int(S.fz[i]) * inv_fscale;
         if (with_post) {
             const int fail = post_force<true>(a, i, S.pos[i], S.vx[i], S.vy[i], S.vz[i], fx, fy, fz, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), eval, e_wall);
             if (fail) atomicOr(&S.misc[M_FAIL], fail);

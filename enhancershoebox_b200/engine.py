@@ -414,10 +414,11 @@ class ShoeboxBatch:
         return st
 
     def counters(self):
-        out = np.empty((self.R, 11), np.int64)
+        out = np.empty((self.R, 12), np.int64)
         self._check(self.lib.esb_get_counters(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
         return dict(evals=out[:, 0], builds=out[:, 1], pairs=out[:, 2], listed=out[:, 3], steps=out[:, 4], total_active=out[:, 5],
-                    cyc_atom=out[:, 6], cyc_build=out[:, 7], cyc_force=out[:, 8], cyc_other=out[:, 9], dangerous=out[:, 10])
+                    cyc_atom=out[:, 6], cyc_build=out[:, 7], cyc_force=out[:, 8], cyc_other=out[:, 9], dangerous=out[:, 10],
+                    max_pair_force=out[:, 11] / 256.0)
 
     def reset_counters(self):
         self._check(self.lib.esb_reset_counters(self.h))

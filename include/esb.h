@@ -25,7 +25,7 @@ extern "C" {
 #define ESB_MAXT 12          /* atom types are 1..11 (run_single_shoebox.py:23-33); index 0 unused */
 #define ESB_MAX_TABLES 48
 #define ESB_N_SHELL 50       /* cluster_r = linspace(0.65, 2.5, 50) (run_single_shoebox.py:425)    */
-#define ESB_N_COUNTERS 11
+#define ESB_N_COUNTERS 12
 #define ESB_FRAME_DOUBLES 9  /* geneTrack.txt columns (run_single_shoebox.py:1496)                   */
 
 enum {
@@ -203,7 +203,8 @@ int esb_get_status(esb_handle *h, int *status);                   /* [R] ESB_ST_
  * pairs summed over evaluations, steps, total_active_steps, then SM cycles spent in the per-atom
  * phase, list builds, force phase, set-up/observation, and the number of "dangerous builds" (a list
  * build that was already due at the first step `neigh_modify delay` permits: what LAMMPS prints at the end
- * of a run) */
+ * of a run), and the largest pair-force component any bead has seen, in units of 2^-8 (the pair forces are
+ * accumulated in fixed point: this is the headroom diagnostic) */
 int esb_get_counters(esb_handle *h, int64_t *out);
 int esb_reset_counters(esb_handle *h);
 /* current bond r0 (after fix adapt) and MD step per handle */

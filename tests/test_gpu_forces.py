@@ -71,8 +71,9 @@ def test_bin_index_is_exact(eng, orc, snapshots):
     eng.upload_state(np.stack([x] * 3), np.stack([v] * 3), np.stack([t] * 3))
     fg, _ = eng.forces("B", use_arrays=True)
     # one flipped bin on a strongly repulsive pair (F ~ 50, neighbouring bins differ by ~1e-4 relative)
-    # would show up as ~4e-5 of the largest force; fp32 accumulation alone stays below 1e-6
-    assert np.abs(fg[0] - fo).max() / np.abs(fo).max() < 1e-6
+    # would show up as ~4e-5 of the largest force; fp32 table values and the fixed-point accumulation (2^-16 per
+    # pair and component, ~60 pairs per bead: ~1e-4 absolute at worst) stay below 3e-6
+    assert np.abs(fg[0] - fo).max() / np.abs(fo).max() < 3e-6
 
 
 def test_pairs_excluded_and_counted(eng, orc, snapshots, box11):
