@@ -106,6 +106,7 @@ struct esb_handle {
     float4 *d_bref4 = nullptr;
     unsigned int *d_nl_pool = nullptr;
     uint2 *d_nl_qinfo = nullptr;
+    int *d_nl_levels = nullptr;
     esb_chunk_desc *d_descs = nullptr;
     int *d_enh = nullptr, *d_s5p = nullptr;
     double *d_cluster_r = nullptr;
@@ -309,7 +310,7 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     k.tabs = array_flavour ? h->d_tabs_array : h->d_tabs_closed;
     k.n_tables = (int)h->tables.size();
     k.tabval = h->d_tabval; k.tabe = h->d_tabe; k.tlm1 = h->tlm1;
-    k.nl_pool = h->d_nl_pool; k.nl_qinfo = h->d_nl_qinfo;
+    k.nl_pool = h->d_nl_pool; k.nl_qinfo = h->d_nl_qinfo; k.nl_levels = h->d_nl_levels;
     // 16-bit list entries need the table id in 5 bits and the bead index in 11 (always true: n_pad <= ESB_NL_STRIDE)
     k.pack16 = getenv("ESB_PACK16") ? atoi(getenv("ESB_PACK16")) != 0 && h->tables.size() <= 32 : h->tables.size() <= 32;
     memcpy(k.class_of, k_class_of, ESB_MAXT);
@@ -366,7 +367,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     const size_t tot = (size_t)n_replicas * h->n_pad;
     if ((rc = dev_alloc(&h->d_pos4, tot)) || (rc = dev_alloc(&h->d_vel4, tot)) || (rc = dev_alloc(&h->d_bref4, tot)) || (rc = dev_alloc(&h->d_rs, (size_t)n_replicas)) ||
         (rc = dev_alloc(&h->d_frozen, (size_t)h->n_pad)) || (rc = dev_alloc(&h->d_nl_pool, (size_t)n_replicas * h->n_pad * ESB_NL_STRIDE + 1024)) ||
-        (rc = dev_alloc(&h->d_nl_qinfo, 2 * tot)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * ESB_N_COUNTERS)) || (rc = dev_alloc(&h->d_sched, (size_t)n_replicas + 1))) {
+        (rc = dev_alloc(&h->d_nl_qinfo, 2 * tot)) || (rc = dev_alloc(&h->d_nl_levels, (size_t)n_replicas * 64)) || (rc = dev_alloc(&h->d_counters, (size_t)n_replicas * ESB_N_COUNTERS)) || (rc = dev_alloc(&h->d_sched, (size_t)n_replicas + 1))) {
         esb_destroy(h);
         return rc;
     }
@@ -391,7 +392,7 @@ int esb_destroy(esb_handle *h)
     cudaSetDevice(h->device);
     cudaFree(h->d_pos4); cudaFree(h->d_vel4); cudaFree(h->d_rs); cudaFree(h->d_frozen); cudaFree(h->d_bterm);
     cudaFree(h->d_spec); cudaFree(h->d_setups); cudaFree(h->d_tabs_closed); cudaFree(h->d_tabs_array);
-    cudaFree(h->d_tabval); cudaFree(h->d_tabe); cudaFree(h->d_nl_pool); cudaFree(h->d_nl_qinfo); cudaFree(h->d_descs);
+    cudaFree(h->d_tabval); cudaFree(h->d_tabe); cudaFree(h->d_nl_pool); cudaFree(h->d_nl_qinfo); cudaFree(h->d_nl_levels); cudaFree(h->d_descs);
     cudaFree(h->d_enh); cudaFree(h->d_s5p); cudaFree(h->d_cluster_r); cudaFree(h->d_frames); cudaFree(h->d_rawd); cudaFree(h->d_hist);
     cudaFree(h->d_counters); cudaFree(h->d_sched); cudaFree(h->d_bref4);
     cudaFree(h->d_mic);

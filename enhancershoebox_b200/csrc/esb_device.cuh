@@ -18,7 +18,13 @@
 #ifndef ESB_MIN_CTAS
 #define ESB_MIN_CTAS 2                  // resident CTAs per SM the step kernel is compiled for (2 x 16 warps: 64 registers)
 #endif
-#define ESB_G 8                      // lanes cooperating on one atom (pair loop and list build)
+#ifndef ESB_G
+#if defined(ESB_CLUSTER) && ESB_CLUSTER
+#define ESB_G 8                      // lanes cooperating on one bead in the pair loop: 8 with the full list of the cluster variant,
+#else
+#define ESB_G 4                      // 4 with the half list (half as many entries per bead: 8 beads per warp)
+#endif
+#endif
 #define ESB_GROUPS (ESB_THREADS / ESB_G)
 #define ESB_MAX_TERMS 8              // bonded terms per atom (linear chain: 2 bonds + 3 angles)
 #define ESB_MAX_SPEC 8               // excluded partners per atom (linear chain: 6)
@@ -124,6 +130,7 @@ struct KArgs {
     const float *tabe;        // energy arrays (hook)
     int tlm1;
     unsigned int *nl_pool;    // [R][n_pad][ESB_NL_STRIDE]  neighbour index | table id << 16; or two 16-bit entries per word:
+    int *nl_levels;           // [R][64] half list: work items of the force loop per chunk level (running sums), kept for the segments of a chunk
     int pack16;               // 1: 16-bit list entries (neighbour index | table id << 11), possible with at most 32 tables
     uint2 *nl_qinfo;          // [R][2][n_pad] {list start, atom | count << 16}: [0] sorted by list length (force order), [1] slot order (build)
     unsigned char class_of[ESB_MAXT + 4];

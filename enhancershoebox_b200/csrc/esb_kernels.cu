@@ -65,7 +65,8 @@ struct Smem {
 };
 
 enum { M_QCTR = 0 /* next quad of the running build / force loop */, M_FAIL, M_PAIRS, M_CURLIST, M_FMAX /* largest |pair force| of the chunk, 2^-8 units */, M_SCAN /* one per warp */,
-       M_CNT_PROM = M_SCAN + ESB_THREADS / 32, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */,
+       M_LEVEL = M_SCAN + ESB_THREADS / 32 /* 64: work items of the force loop up to and including every chunk level (see build_lists) */,
+       M_CNT_PROM = M_LEVEL + 64, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */,
 #if ESB_CLUSTER
        M_PARITY = M_HIST + 52 /* which of the two position buffers is current */, M_NMINE /* beads this CTA owns */, M_VOTE /* rebuild vote [parity][rank] */,
        M_CFAIL = M_VOTE + 16 /* failure bits [parity][rank] */, M_END = M_CFAIL + 16 };
@@ -181,6 +182,19 @@ __device__ __forceinline__ float4 lds128(const unsigned int addr)
 // pair contributes at most ~365.  A bead whose sum leaves half the range (16384) flags the replica (ESB_ST_NONFINITE)
 // in the per-atom phase; counter 11 reports the largest sum seen.
 #define ESB_FSCALE 0x1p16f
+// Work items of the half-list force loop: a quad (32 / ESB_G beads, consecutive in the order of decreasing list length) times a
+// CHUNK of its lists, ESB_ITEM_ROUNDS entries per lane.  A bead whose list is longer than a chunk is finished by other
+// warps: every item adds its part of bead i's force with the same integer atomics that reach bead j, so the items are
+// independent and the phase no longer waits for the warp that drew the longest lists (those of the Ser5P cluster are
+// ten times the median).  Level c = the c-th chunk of every quad that has one; the lengths are sorted, so level c is the
+// first Q_c quads and item t is found from the running sums of Q_c.
+#ifndef ESB_ITEM_ROUNDS
+#define ESB_ITEM_ROUNDS 8
+#endif
+#define ESB_CHUNK (ESB_ITEM_ROUNDS * ESB_G)      // entries of one bead per item
+#ifndef ESB_CUT32
+#define ESB_CUT32 1
+#endif
 #ifndef ESB_FGUARD
 #define ESB_FGUARD 1
 #endif
@@ -345,9 +359,8 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
 
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    // P16 (at most 32 tables): 16-bit entries (neighbour | table id << 11), two per word -- word 8*(e/16) + e%8 holds
-    // entries e (low half) and e + 8 (high half) of a block of 16, so that lane g of a bead's group reads its entries
-    // g and g + 8 with one load and sums in the same order as with 32-bit entries; half the list traffic
+    // P16 (at most 32 tables): 16-bit entries (neighbour | table id << 11), two per word, in list order (the integer
+    // force sums do not depend on the order in which a group's lanes visit the entries); half the list traffic
     constexpr unsigned int ESTRIDE = P16 ? ESB_NL_STRIDE / 2 : ESB_NL_STRIDE;      // arena of a bead in words
     unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESTRIDE;
     unsigned short *pool16 = reinterpret_cast<unsigned short *>(pool);
@@ -507,7 +520,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
                         if (bits) {                                  // warp-uniform: most candidates are rejected by every bead
                             const int at = cnt[b] + __popc(bits & lt_mask);
                             if (ok && at < ESB_NL_MAXNB) {
-                                if (P16) pool16[(unsigned int)ia[b] * ESB_NL_STRIDE + ((at & ~15) | ((at & 7) << 1) | ((at >> 3) & 1))] =
+                                if (P16) pool16[(unsigned int)ia[b] * ESB_NL_STRIDE + at] =
                                              (unsigned short)(UNIFORM ? ent_u : ((unsigned int)j | ((unsigned int)tab_row[ta[b] * ESB_MAXT + tj] << 11)));
                                 else pool[(unsigned int)ia[b] * ESB_NL_STRIDE + at] = UNIFORM ? ent_u : ((unsigned int)j | ((unsigned int)tab_row[ta[b] * ESB_MAXT + tj] << 16));
                             }
@@ -564,13 +577,33 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
 #pragma unroll
         for (int k = 0; k < PER; k++) { if (PER * tid + k <= ESB_NL_MAXNB) hist[PER * tid + k] = base; base += v[k]; }
         __syncthreads();
+#if ESB_HALF
+        // hist[ESB_NL_MAXNB - L] = beads with a list longer than L = the beads of chunk level L / ESB_CHUNK
+        if (tid < 64) {
+            const int L = tid * ESB_CHUNK;
+            const int beads = L <= ESB_NL_MAXNB ? hist[ESB_NL_MAXNB - L] : 0;
+            S.misc[M_LEVEL + tid] = (beads + 32 / ESB_G - 1) / (32 / ESB_G);       // quads of this level
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int v0 = S.misc[M_LEVEL + lane], v1 = S.misc[M_LEVEL + 32 + lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t0 = __shfl_up_sync(FULL, v0, d), t1 = __shfl_up_sync(FULL, v1, d);
+                if (lane >= d) { v0 += t0; v1 += t1; }
+            }
+            v1 += __shfl_sync(FULL, v0, 31);
+            S.misc[M_LEVEL + lane] = v0; S.misc[M_LEVEL + 32 + lane] = v1;
+            a.nl_levels[(size_t)r * 64 + lane] = v0; a.nl_levels[(size_t)r * 64 + 32 + lane] = v1;       // (for a later segment of the chunk)
+        }
+#endif
         for (int k = tid; k < n; k += ESB_THREADS) {
             const uint2 d = __ldcg(&qbuild[k]);
             const int at = atomicAdd(&hist[ESB_NL_MAXNB - (int)(d.y >> 16)], 1);
             qforce[at] = d;
 #if ESB_CLUSTER
             // the CTA that takes force quad at/4 owns the bead: bonded terms, pair loop, integration
-            for (int rk = 0; rk < csize(); rk++) peer(S.owner, rk)[d.y & 0xffffu] = (unsigned char)((at >> 2) % csize());
+            for (int rk = 0; rk < csize(); rk++) peer(S.owner, rk)[d.y & 0xffffu] = (unsigned char)((at / (32 / ESB_G)) % csize());
 #endif
         }
     }
@@ -684,6 +717,15 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
 //         the bin midpoint (ljsoft_potential.py:10-16) inside [p0hi, plo) and the LOOKUP array
 //         entry elsewhere.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lds32f(const unsigned int addr)
+{
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// r^2 with a fixed operation order: the soft-phase force depends on its last bit, and every kernel variant must agree
+__device__ __forceinline__ float dist_sq(const float dx, const float dy, const float dz) { return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))); }
+
 template <int NP, int MODE, bool ENERGY, bool P16>
 __device__ __noinline__ void force_phase(const KArgs &a, const int r, const float soft_a, const float r0_1, const float r0_2,
                                          double *energy /* [3] pair, bond, angle: per-thread partials (ENERGY only) */)
@@ -713,23 +755,45 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
     unsigned int npairs = 0;
     // quads in order of decreasing list length, handed out dynamically (longest first: the warps finish
     // together); the next quad's descriptor is fetched (L2) while the current one is processed
-    const int nquads = (n + 3) >> 2;
+    constexpr int BPW = 32 / ESB_G;                               // beads per warp: a "quad" of the force loop
+#if ESB_HALF
+    // work items (quad, chunk level): see ESB_CHUNK.  Lane l keeps the items up to and including levels l and l + 32.
+    const int lev_lo = S.misc[M_LEVEL + lane], lev_hi = S.misc[M_LEVEL + 32 + lane];
+    const int nquads = __shfl_sync(FULL, lev_hi, 31);             // (= number of items)
+    int e_base = 0, e_base_next = 0;
+    auto next_quad = [&]() {                                      // returns the quad of the next item, its level in e_base_next
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&S.misc[M_QCTR], 1);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= nquads) return 0x7fffffff;
+        const int lev = __popc(__ballot_sync(FULL, t >= lev_lo)) + __popc(__ballot_sync(FULL, t >= lev_hi));
+        e_base_next = lev * ESB_CHUNK;
+        return t - (lev ? S.misc[M_LEVEL + lev - 1] : 0);
+    };
+#else
+    const int nquads = (n + BPW - 1) / BPW;
+    constexpr int e_base = 0;
     auto next_quad = [&]() {
         int t = 0;
         if (lane == 0) t = atomicAdd(&S.misc[M_QCTR], 1);
         return __shfl_sync(FULL, t, 0) * csize() + crank();
     };
+#endif
     int q = next_quad();
+#if ESB_HALF
+    e_base = e_base_next;
+#endif
     uint2 qi = make_uint2(0u, 0u);
-    if (q < nquads && 4 * q + grp < n) qi = __ldcg(&qinfo[4 * q + grp]);
+    if (q < nquads && BPW * q + grp < n) qi = __ldcg(&qinfo[BPW * q + grp]);
     while (q < nquads) {
         const int qn = next_quad();
         uint2 qi_next = make_uint2(0u, 0u);
-        if (qn < nquads && 4 * qn + grp < n) qi_next = __ldcg(&qinfo[4 * qn + grp]);
-        const bool valid = 4 * q + grp < n;
+        if (qn < nquads && BPW * qn + grp < n) qi_next = __ldcg(&qinfo[BPW * qn + grp]);
+        const bool valid = BPW * q + grp < n;
         const int i = (int)(qi.y & 0xffffu);
-        const int cnt = valid ? (int)(qi.y >> 16) : 0;
-        const unsigned int *nl = pool + qi.x;
+        // this item's part of the list: entries [e_base, e_base + ESB_CHUNK) (half list) or all of it
+        const int cnt = valid ? (ESB_HALF ? min(max((int)(qi.y >> 16) - e_base, 0), ESB_CHUNK) : (int)(qi.y >> 16)) : 0;
+        const unsigned int *nl = pool + qi.x + (P16 ? e_base / 2 : e_base);
         const float4 pi = lds128(sb + 16u * (unsigned int)i);
         const int cnt_max = __reduce_max_sync(FULL, cnt);
         int fx = 0, fy = 0, fz = 0;                               // fixed point, ESB_FSCALE_* counts per force unit
@@ -742,7 +806,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
             if (e < cnt) {
                 const float4 pj = lds128(sb + 16u * (ent & (P16 ? 0x7ffu : 0xffffu)));
                 const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                const float r2 = dx * dx + dy * dy + dz * dz;
+                const float r2 = dist_sq(dx, dy, dz);
                 float fpair;
                 if (MODE == 1) {
                     const int ti = __float_as_int(pi.w) & 0xff, tj = __float_as_int(pj.w) & 0xff;
@@ -757,8 +821,13 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                 } else {
                     const unsigned int tb = P16 ? (ent >> 11) & 0x1fu : ent >> 16;   // table id of the pair (fixed between builds)
                     const unsigned int T4 = tbase + 48u * tb;                         // DevTab = 3 float4 words
+#if ESB_CUT32
+                    if (!(r2 < lds32f(T4))) return;                                   // cutsq (one word: a quarter of the wavefronts of the full row)
+                    const float4 t0 = lds128(T4);                                     // cutsq, invdelta_f, delta, innersq_f
+#else
                     const float4 t0 = lds128(T4);                                     // cutsq, invdelta_f, delta, innersq_f
                     if (!(r2 < t0.x)) return;
+#endif
                     const float4 t1 = lds128(T4 + 16u);                               // K, is6, c, patch
                     const float u = (r2 - t0.w) * t0.y;
                     int it = (int)u;
@@ -799,8 +868,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
         unsigned int w[DEPTH];
 #pragma unroll
         for (int k = 0; k < DEPTH; k++) w[k] = __ldcg(lp + k * ESB_G);
-        if (P16) {                                                // one word = the lane's entries e0 + gl and e0 + 8 + gl
-            static_assert(ESB_G == 8, "16-bit list layout: blocks of 2 x 8 entries");
+        if (P16) {                                                // word wi of the list = its entries 2 wi and 2 wi + 1
             for (int e0 = 0; e0 < cnt_max; e0 += DEPTH * 2 * ESB_G) {
                 lp += DEPTH * ESB_G;
 #pragma unroll
@@ -808,7 +876,8 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
                     if (k > 0 && e0 + k * 2 * ESB_G >= cnt_max) break;
                     const unsigned int c = w[k];
                     w[k] = __ldcg(lp + k * ESB_G);
-                    pair_body(c, e0 + k * 2 * ESB_G + gl); pair_body(c >> 16, e0 + (2 * k + 1) * ESB_G + gl);
+                    const int e = e0 + 2 * (k * ESB_G + gl);
+                    pair_body(c, e); pair_body(c >> 16, e + 1);
                 }
             }
         } else {
@@ -834,6 +903,9 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
             else { S.fx[i] = __int_as_float(fx); S.fy[i] = __int_as_float(fy); S.fz[i] = __int_as_float(fz); }
         }
         q = qn; qi = qi_next;
+#if ESB_HALF
+        e_base = e_base_next;
+#endif
     }
     if (npairs) atomicAdd(&S.misc[M_PAIRS], (int)npairs);
     if (ENERGY) { energy[0] += e_pair; energy[1] += e_bond; energy[2] += e_angle; }
@@ -1476,7 +1548,9 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             S.vx[k] = v.x; S.vy[k] = v.y; S.vz[k] = v.z;
             S.fx[k] = 0.0f; S.fy[k] = 0.0f; S.fz[k] = 0.0f;       // (a segment that continues a chunk starts without a build)
         }
-        for (int k = tid; k < M_END; k += ESB_THREADS) S.misc[k] = (SEG && k == M_CURLIST && it0 > 0) ? rs.curlist : 0;
+        for (int k = tid; k < M_END; k += ESB_THREADS)
+            S.misc[k] = (SEG && it0 > 0 && k == M_CURLIST) ? rs.curlist
+                        : (SEG && ESB_HALF && it0 > 0 && k >= M_LEVEL && k < M_LEVEL + 64) ? __ldcg(&a.nl_levels[(size_t)r * 64 + (k - M_LEVEL)]) : 0;
         const uint32_t k0 = (uint32_t)rs.seed, k1 = (uint32_t)(rs.seed >> 32);
         long long *const L = reinterpret_cast<long long *>(S.dmisc);          // L_* slots: touched by thread 0 only
         if (tid == 0) { for (int k = L_EVALS; k < L_TMARK; k++) L[k] = 0; L[L_TMARK] = clock64(); }
