@@ -50,6 +50,14 @@ int fail(int code, const char *fmt, ...)
         if (e_ != cudaSuccess) return fail(ESB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// temporary device buffer of a host-facing call: freed on every return path
+template <class T>
+struct Scratch {
+    T *p = nullptr;
+    ~Scratch() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T)); }
+};
+
 template <class T>
 int dev_alloc(T **p, size_t count)
 {
@@ -127,6 +135,11 @@ struct esb_handle {
     int mic_n[3] = {0, 0, 0}, mic_frames = 0;
     unsigned short *d_mic = nullptr;
     int n_sm = 148;
+    int n_seg = 0;                 // esb_set_segments
+    std::vector<esb_chunk_desc> descs_host;      // the schedule, for validation at run time
+    cudaStream_t last_stream = nullptr;          // stream of the last esb_run: the blocking getters wait for it
+    bool run_pending = false;
+    int force_wide = -1;           // esb_set_segments: CTA width of the step kernel (-1: by batch size)
     size_t smem_per_sm = 233472;
     Layout lay = {0, 0, 0, 0};
     std::vector<ReplicaScalars> rs_host;
@@ -134,6 +147,17 @@ struct esb_handle {
 };
 
 namespace {
+
+// esb_run is asynchronous on the caller's stream; the getters below copy on the legacy default stream, which does not
+// wait for a cudaStreamNonBlocking stream: wait for the last run explicitly.
+int wait_for_run(esb_handle *h)
+{
+    if (h->run_pending) {
+        CK(cudaStreamSynchronize(h->last_stream));
+        h->run_pending = false;
+    }
+    return ESB_OK;
+}
 
 int check_device(int device)
 {
@@ -328,6 +352,7 @@ int push_rs(esb_handle *h)
 }
 int pull_rs(esb_handle *h)
 {
+    { const int rc_ = wait_for_run(h); if (rc_) return rc_; }
     CK(cudaMemcpy(h->rs_host.data(), h->d_rs, sizeof(ReplicaScalars) * h->R, cudaMemcpyDeviceToHost));
     return ESB_OK;
 }
@@ -585,6 +610,7 @@ int esb_get_actin(esb_handle *h, int *plus, int *minus, int *n_free, int *free_l
 {
     if (!h || !h->have_actin) return fail(ESB_ESTATE, "esb_set_actin has not been called");
     CK(cudaSetDevice(h->device));
+    { const int rc_ = wait_for_run(h); if (rc_) return rc_; }
     const int count = h->act.count;
     std::vector<unsigned int> link((size_t)h->R * count);
     std::vector<unsigned short> lists((size_t)h->R * ESB_ACT_WORDS(count));
@@ -611,6 +637,7 @@ int esb_get_actin_frames(esb_handle *h, int chunk_begin, int n_chunks, int *stat
     if (!h->have_actin || !h->d_act_stats) return fail(ESB_ESTATE, "no actin records (esb_set_actin + esb_set_schedule first)");
     if (chunk_begin < 0 || n_chunks < 1 || chunk_begin + n_chunks > h->n_chunks) return fail(ESB_EINVAL, "chunk range outside the schedule");
     CK(cudaSetDevice(h->device));
+    { const int rc_ = wait_for_run(h); if (rc_) return rc_; }
     CK(cudaMemcpy2D(stats, (size_t)n_chunks * 6 * sizeof(int), h->d_act_stats + (size_t)chunk_begin * 6, (size_t)h->n_chunks * 6 * sizeof(int),
                     (size_t)n_chunks * 6 * sizeof(int), h->R, cudaMemcpyDeviceToHost));
     if (hist) {
@@ -650,6 +677,7 @@ int esb_get_microscopy(esb_handle *h, int frame_begin, int n_frames, unsigned sh
     if (!h->d_mic) return fail(ESB_ESTATE, "esb_set_microscopy has not been called");
     if (frame_begin < 0 || n_frames < 1 || frame_begin + n_frames > h->mic_frames) return fail(ESB_EINVAL, "frame range outside the buffer");
     CK(cudaSetDevice(h->device));
+    { const int rc_ = wait_for_run(h); if (rc_) return rc_; }
     const size_t per = (size_t)5 * (h->mic_n[0] - 1) * (h->mic_n[1] - 1) * (h->mic_n[2] - 1) * sizeof(unsigned short);
     CK(cudaMemcpy2D(out, (size_t)n_frames * per, h->d_mic + (size_t)frame_begin * per / sizeof(unsigned short), (size_t)h->mic_frames * per,
                     (size_t)n_frames * per, h->R, cudaMemcpyDeviceToHost));
@@ -806,21 +834,21 @@ int esb_upload_state(esb_handle *h, const double *x, const double *v, const int 
 {
     if (!h || !x || !types) return fail(ESB_EINVAL, "NULL argument");
     CK(cudaSetDevice(h->device));
+    { const int rc_ = wait_for_run(h); if (rc_) return rc_; }
     const size_t nsrc = (size_t)(replicate ? 1 : h->R) * h->N;
-    double *dx = nullptr, *dv = nullptr;
-    int *dt = nullptr;
-    CK(cudaMalloc(&dx, nsrc * 3 * sizeof(double)));
-    CK(cudaMalloc(&dt, nsrc * sizeof(int)));
-    CK(cudaMemcpy(dx, x, nsrc * 3 * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dt, types, nsrc * sizeof(int), cudaMemcpyHostToDevice));
+    Scratch<double> dx, dv;
+    Scratch<int> dt;
+    CK(dx.alloc(nsrc * 3));
+    CK(dt.alloc(nsrc));
+    CK(cudaMemcpy(dx.p, x, nsrc * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dt.p, types, nsrc * sizeof(int), cudaMemcpyHostToDevice));
     if (v) {
-        CK(cudaMalloc(&dv, nsrc * 3 * sizeof(double)));
-        CK(cudaMemcpy(dv, v, nsrc * 3 * sizeof(double), cudaMemcpyHostToDevice));
+        CK(dv.alloc(nsrc * 3));
+        CK(cudaMemcpy(dv.p, v, nsrc * 3 * sizeof(double), cudaMemcpyHostToDevice));
     }
-    esb_pack_kernel<<<512, 256>>>(dx, dv, dt, h->d_frozen, h->d_pos4, h->d_vel4, h->N, h->n_pad, h->R, replicate);
+    esb_pack_kernel<<<512, 256>>>(dx.p, dv.p, dt.p, h->d_frozen, h->d_pos4, h->d_vel4, h->N, h->n_pad, h->R, replicate);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    cudaFree(dx); cudaFree(dv); cudaFree(dt);
     h->have_state = true;
     return ESB_OK;
 }
@@ -829,18 +857,18 @@ int esb_download_state(esb_handle *h, double *x, double *v, int *types)
 {
     if (!h) return fail(ESB_EINVAL, "NULL handle");
     CK(cudaSetDevice(h->device));
+    { const int rc_ = wait_for_run(h); if (rc_) return rc_; }
     const size_t n = (size_t)h->R * h->N;
-    double *dx = nullptr, *dv = nullptr;
-    int *dt = nullptr;
-    if (x) CK(cudaMalloc(&dx, n * 3 * sizeof(double)));
-    if (v) CK(cudaMalloc(&dv, n * 3 * sizeof(double)));
-    if (types) CK(cudaMalloc(&dt, n * sizeof(int)));
-    esb_unpack_kernel<<<512, 256>>>(h->d_pos4, h->d_vel4, dx, dv, dt, h->N, h->n_pad, h->R);
+    Scratch<double> dx, dv;
+    Scratch<int> dt;
+    if (x) CK(dx.alloc(n * 3));
+    if (v) CK(dv.alloc(n * 3));
+    if (types) CK(dt.alloc(n));
+    esb_unpack_kernel<<<512, 256>>>(h->d_pos4, h->d_vel4, dx.p, dv.p, dt.p, h->N, h->n_pad, h->R);
     CK(cudaGetLastError());
-    if (x) CK(cudaMemcpy(x, dx, n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
-    if (v) CK(cudaMemcpy(v, dv, n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
-    if (types) CK(cudaMemcpy(types, dt, n * sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(dx); cudaFree(dv); cudaFree(dt);
+    if (x) CK(cudaMemcpy(x, dx.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (v) CK(cudaMemcpy(v, dv.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (types) CK(cudaMemcpy(types, dt.p, n * sizeof(int), cudaMemcpyDeviceToHost));
     return ESB_OK;
 }
 
@@ -899,7 +927,7 @@ int esb_set_schedule(esb_handle *h, int n_chunks, const esb_chunk_desc *descs)
         CK(cudaMemset(h->d_act_hist, 0, (size_t)h->R * n_chunks * (ESB_N_SHELL - 1) * sizeof(unsigned short)));
     }
     h->n_chunks = n_chunks;
-    // keep a host copy for validation at run time
+    h->descs_host = v;             // validated against the pair set-ups at run time
     return ESB_OK;
 }
 
@@ -928,17 +956,23 @@ int esb_run(esb_handle *h, int chunk_begin, int n_chunks, void *stream)
     size_t smem = 0;
     int rc = prepare_launch(h, &smem);
     if (rc) return rc;
+    for (int c = chunk_begin; c < chunk_begin + n_chunks; c++) {      // a chunk whose pair set-up was never provided would run without pair forces
+        const esb_chunk_desc &d = h->descs_host[c];
+        if (d.pair_mode == 1 && !h->have_soft) return fail(ESB_ESTATE, "chunk %d runs pair_style soft but esb_set_soft was not called", c);
+        if (d.pair_mode == 2 && (!h->have_tables || !h->have_map[d.map_id]))
+            return fail(ESB_ESTATE, "chunk %d runs pair_style table with map %d but %s", c, d.map_id, h->have_tables ? "that map was not set (esb_set_table_map)" : "no tables were set (esb_set_tables)");
+    }
     KArgs k;
     fill_kargs(h, k, false);
     // a batch that cannot fill the device with two CTAs per SM gets the 32-warp CTA: a replica then advances twice as fast
-    const int n_seg = getenv("ESB_SEG") ? atoi(getenv("ESB_SEG")) : 0;      // 0: the launcher decides
+    const int n_seg = getenv("ESB_SEG") ? atoi(getenv("ESB_SEG")) : h->n_seg;      // 0: the launcher decides
     // (also a system too large for two 16-warp CTAs per SM -- more than ~1700 beads: one 32-warp CTA fills the SM better than one 16-warp CTA)
     const bool two_fit = 2 * (smem + 1024) <= h->smem_per_sm;
-    const bool wide = getenv("ESB_WIDE") ? atoi(getenv("ESB_WIDE")) != 0 : (h->R <= h->n_sm || !two_fit);
+    const bool wide = getenv("ESB_WIDE") ? atoi(getenv("ESB_WIDE")) != 0 : h->force_wide >= 0 ? (h->force_wide != 0 || !two_fit) : (h->R <= h->n_sm || !two_fit);
     // even smaller batches: a thread-block cluster of 2, 4 or 8 CTAs (SMs) per replica
     int cluster = 1;
     if (getenv("ESB_CLUSTER_SIZE")) cluster = atoi(getenv("ESB_CLUSTER_SIZE"));
-    else if (wide && h->R <= h->n_sm) for (int c = 8; c >= 2; c >>= 1) if ((long long)h->R * c <= (long long)h->n_sm * 7 / 8) { cluster = c; break; }
+    else if (wide && h->force_wide < 0 && h->R <= h->n_sm) for (int c = 8; c >= 2; c >>= 1) if ((long long)h->R * c <= (long long)h->n_sm * 7 / 8) { cluster = c; break; }
     if (cluster == 2 || cluster == 4 || cluster == 8) {
         const size_t smem_c = esb_smem_bytes_v2048(h->n_pad, (int)h->tables.size(), h->n_topo_pad);
         CK(esb_launch_run_v2048(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem_c, (cudaStream_t)stream, h->d_sched, h->n_sm, cluster));
@@ -948,6 +982,17 @@ int esb_run(esb_handle *h, int chunk_begin, int n_chunks, void *stream)
     } else {
         CK(esb_launch_run_v512(k, chunk_begin, n_chunks, 0.03 * 200, 60.0, smem, (cudaStream_t)stream, h->d_sched, h->n_sm, n_seg));
     }
+    h->last_stream = (cudaStream_t)stream;
+    h->run_pending = true;
+    return ESB_OK;
+}
+
+int esb_set_segments(esb_handle *h, int n_seg, int co_scheduled)
+{
+    if (!h) return fail(ESB_EINVAL, "NULL handle");
+    if (n_seg < 0 || n_seg > 64) return fail(ESB_EINVAL, "n_seg %d outside [0, 64]", n_seg);
+    h->n_seg = n_seg;
+    h->force_wide = co_scheduled ? 0 : -1;
     return ESB_OK;
 }
 
@@ -965,6 +1010,7 @@ int esb_forces(esb_handle *h, int pair_mode, int map_id, double soft_a, int with
     if (!h || !f_out) return fail(ESB_EINVAL, "NULL argument");
     if (pair_mode < 0 || pair_mode > 2 || map_id < 0 || map_id >= 4) return fail(ESB_EINVAL, "bad pair_mode/map_id");
     CK(cudaSetDevice(h->device));
+    { const int rc_ = wait_for_run(h); if (rc_) return rc_; }
     size_t smem = 0;
     int rc = prepare_launch(h, &smem);
     if (rc) return rc;
@@ -972,14 +1018,13 @@ int esb_forces(esb_handle *h, int pair_mode, int map_id, double soft_a, int with
     if (pair_mode == 1 && !h->have_soft) return fail(ESB_ESTATE, "soft cutoffs not set");
     KArgs k;
     fill_kargs(h, k, use_arrays != 0);
-    double *df = nullptr, *de = nullptr;
-    CK(cudaMalloc(&df, (size_t)h->R * h->N * 3 * sizeof(double)));
-    CK(cudaMalloc(&de, (size_t)h->R * 4 * sizeof(double)));
+    Scratch<double> df, de;
+    CK(df.alloc((size_t)h->R * h->N * 3));
+    CK(de.alloc((size_t)h->R * 4));
     const int setup_id = pair_mode == 2 ? 1 + map_id + (use_arrays ? 4 : 0) : 0;
-    CK(esb_launch_forces(k, pair_mode, setup_id, (float)soft_a, with_post, eval, df, de, smem, 0));
-    CK(cudaMemcpy(f_out, df, (size_t)h->R * h->N * 3 * sizeof(double), cudaMemcpyDeviceToHost));
-    if (e_out) CK(cudaMemcpy(e_out, de, (size_t)h->R * 4 * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(df); cudaFree(de);
+    CK(esb_launch_forces(k, pair_mode, setup_id, (float)soft_a, with_post, eval, df.p, de.p, smem, 0));
+    CK(cudaMemcpy(f_out, df.p, (size_t)h->R * h->N * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (e_out) CK(cudaMemcpy(e_out, de.p, (size_t)h->R * 4 * sizeof(double), cudaMemcpyDeviceToHost));
     return ESB_OK;
 }
 
@@ -988,6 +1033,7 @@ int esb_get_frames(esb_handle *h, int chunk_begin, int n_chunks, double *out, in
     if (!h || !out) return fail(ESB_EINVAL, "NULL argument");
     if (chunk_begin < 0 || n_chunks < 1 || chunk_begin + n_chunks > h->n_chunks) return fail(ESB_EINVAL, "chunk range outside the schedule");
     CK(cudaSetDevice(h->device));
+    { const int rc_ = wait_for_run(h); if (rc_) return rc_; }
     CK(cudaMemcpy2D(out, (size_t)n_chunks * ESB_FRAME_DOUBLES * sizeof(double),
                     h->d_frames + (size_t)chunk_begin * ESB_FRAME_DOUBLES, (size_t)h->n_chunks * ESB_FRAME_DOUBLES * sizeof(double),
                     (size_t)n_chunks * ESB_FRAME_DOUBLES * sizeof(double), h->R, cudaMemcpyDeviceToHost));
@@ -1006,6 +1052,7 @@ int esb_get_raw_distances(esb_handle *h, int chunk_begin, int n_chunks, double *
     if (!h || !out) return fail(ESB_EINVAL, "NULL argument");
     if (chunk_begin < 0 || n_chunks < 1 || chunk_begin + n_chunks > h->n_chunks) return fail(ESB_EINVAL, "chunk range outside the schedule");
     CK(cudaSetDevice(h->device));
+    { const int rc_ = wait_for_run(h); if (rc_) return rc_; }
     CK(cudaMemcpy2D(out, (size_t)n_chunks * 2 * sizeof(double), h->d_rawd + (size_t)chunk_begin * 2, (size_t)h->n_chunks * 2 * sizeof(double),
                     (size_t)n_chunks * 2 * sizeof(double), h->R, cudaMemcpyDeviceToHost));
     return ESB_OK;
@@ -1036,6 +1083,7 @@ int esb_get_counters(esb_handle *h, int64_t *out)
 {
     if (!h || !out) return fail(ESB_EINVAL, "NULL argument");
     CK(cudaSetDevice(h->device));
+    { const int rc_ = wait_for_run(h); if (rc_) return rc_; }
     CK(cudaMemcpy(out, h->d_counters, (size_t)h->R * ESB_N_COUNTERS * sizeof(int64_t), cudaMemcpyDeviceToHost));
     return ESB_OK;
 }
@@ -1044,6 +1092,7 @@ int esb_reset_counters(esb_handle *h)
 {
     if (!h) return fail(ESB_EINVAL, "NULL handle");
     CK(cudaSetDevice(h->device));
+    { const int rc_ = wait_for_run(h); if (rc_) return rc_; }
     CK(cudaMemset(h->d_counters, 0, (size_t)h->R * ESB_N_COUNTERS * sizeof(int64_t)));
     return ESB_OK;
 }

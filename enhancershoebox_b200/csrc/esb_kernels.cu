@@ -201,6 +201,7 @@ __device__ __forceinline__ float4 lds128(const unsigned int addr)
 #ifndef ESB_HALF
 #define ESB_HALF (!ESB_CLUSTER)      // the cluster variant deals the quads to several CTAs and keeps the full list (no remote scatter)
 #endif
+static_assert(!ESB_HALF || 64 * ESB_CHUNK > ESB_NL_MAXNB, "64 chunk levels must cover the longest list");
 template <int NP>
 __device__ __forceinline__ unsigned int force_off(const KArgs &a) { return 28u * (unsigned int)(NP ? NP : a.n_pad); }   // byte offset of S.fx
 // f[j] += (vx, vy, vz) for the three SoA force arrays; addr = shared address of fx[j]

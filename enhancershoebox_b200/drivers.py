@@ -135,11 +135,33 @@ def run_condition(driver: str, a: dict, n_chunks: int | None = None, device: int
     return len(failed)
 
 
+def pick_device(repeats, n_devices: int | None = None) -> int:
+    """GPU of this process.  The reference's launchers start one OS process per repeat, 8 or 9 at a time
+    (run_parallel_shoebox.sh:58-76, VisitorGeneMaps/run_singleCond_parallel.sh:38-61): under the UNCHANGED launcher the
+    processes spread over the GPUs of the box by repeat number (repeat % n_gpus).  ESB_DEVICE pins a device;
+    CUDA_VISIBLE_DEVICES narrows the set as usual."""
+    if "ESB_DEVICE" in os.environ:
+        return int(os.environ["ESB_DEVICE"])
+    if n_devices is None:
+        try:
+            import ctypes
+            cudart = ctypes.CDLL("libcudart.so")
+            cnt = ctypes.c_int(0)
+            n_devices = cnt.value if cudart.cudaGetDeviceCount(ctypes.byref(cnt)) == 0 and cnt.value > 0 else 1
+        except OSError:
+            try:
+                import torch
+                n_devices = max(torch.cuda.device_count(), 1)
+            except Exception:
+                n_devices = 1
+    return int(repeats[0]) % max(n_devices, 1)
+
+
 def main_shoebox(argv=None) -> int:
     a = parse_args(sys.argv[1:] if argv is None else argv, with_actin=True)
-    return 1 if run_condition("shoebox", a) else 0
+    return 1 if run_condition("shoebox", a, device=pick_device(a["repeats"])) else 0
 
 
 def main_genes_stages(argv=None, make_microscopy: bool = False) -> int:
     a = parse_args(sys.argv[1:] if argv is None else argv, with_actin=False)
-    return 1 if run_condition("genes_stages", a, make_microscopy=make_microscopy) else 0
+    return 1 if run_condition("genes_stages", a, make_microscopy=make_microscopy, device=pick_device(a["repeats"])) else 0

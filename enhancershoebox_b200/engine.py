@@ -90,6 +90,7 @@ _SIGNATURES = {
     "esb_set_schedule": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ChunkDesc)]),
     "esb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "esb_sync": (C.c_int, [C.c_void_p]),
+    "esb_set_segments": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "esb_forces": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "esb_get_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "esb_get_raw_distances": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
@@ -347,6 +348,10 @@ class ShoeboxBatch:
 
     def sync(self):
         self._check(self.lib.esb_sync(self.h))
+
+    def set_segments(self, n_seg: int = 0, co_scheduled: bool = False):
+        """Scheduling hint for a batch whose launches share the GPU with another batch's (esb.h: esb_set_segments)."""
+        self._check(self.lib.esb_set_segments(self.h, int(n_seg), int(co_scheduled)))
 
     def forces(self, pair: str = "B", soft_a: float = 0.0, with_post: bool = False, eval_index: int = 0, use_arrays: bool = False):
         """Parity hook: forces [R,N,3] and energies [R,4] (pair, bond, angle, wall) at the current state."""

@@ -145,3 +145,15 @@ def summary_csv(groups, rows) -> str:
     if parts:
         df = pd.concat([df] + parts, ignore_index=True)
     return df.to_csv()
+
+
+def summary_cpp_csv(groups, rows) -> str:
+    """summary_contact_grouped_*_cpp.txt as VisitorGeneMaps/dist_genestages_grouped_cpp writes it (binary only; golden
+    VisitorGeneMaps/summary_contact_grouped_Thresholds10-100_cpp.txt): no index column, `ostream << double` with the
+    default precision (6 significant digits = printf %g), and 0 where the Python aggregator leaves the mean of an empty
+    list (DistActivation of a group without activation) as NaN."""
+    lines = ["Promoter,Threshold,Activation,S5PInt,S2PInt,Contact,DistActivation"]
+    for (p, t, a, _), r in zip(groups, rows):
+        vals = ["%g" % (0.0 if np.isnan(v) else v) for v in r]
+        lines.append(",".join([str(int(p)), str(int(t)), str(int(a))] + vals))
+    return "\n".join(lines) + "\n"

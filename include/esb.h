@@ -182,6 +182,12 @@ int esb_set_schedule(esb_handle *h, int n_chunks, const esb_chunk_desc *descs);
  * (a cudaStream_t, may be NULL). */
 int esb_run(esb_handle *h, int chunk_begin, int n_chunks, void *stream);
 int esb_sync(esb_handle *h);
+/* Scheduling hint for launches that SHARE the device with the launch of another handle (two half batches on two
+ * streams, so that one half's host copies overlap the other half's steps): every chunk is cut into n_seg consecutive
+ * work items (same arithmetic, same bits) so that the two persistent kernels interleave at that grain instead of one
+ * waiting for whole chunks of the other; co_scheduled != 0 keeps the two-CTAs-per-SM kernel even for a batch that would
+ * fit one CTA per SM.  n_seg = 0, co_scheduled = 0: the defaults (the launcher decides). */
+int esb_set_segments(esb_handle *h, int n_seg, int co_scheduled);
 
 /* Parity hook: forces [R][N][3] and energies [R][4] = (pair, bond, angle, wall) at the current
  * positions.  pair_mode/map_id as in esb_chunk_desc; soft_a: prefactor A for pair_mode 1.

@@ -187,6 +187,7 @@ typedef struct esbo_system {
     double soft_a, soft_cut[ESBO_MAXT * ESBO_MAXT];
     int ntables, tlm1;
     double *tab_f, *tab_e, *tab_innersq, *tab_delta, *tab_invdelta, *tab_cut;
+    int tab_shared;            /* tab_f / tab_e belong to the caller */
     int tabmap[ESBO_MAXT * ESBO_MAXT];
     /* adapt */
     int nadapt;
@@ -232,7 +233,8 @@ void esbo_destroy(esbo_system *s)
     if (!s) return;
     free(s->x); free(s->v); free(s->f); free(s->x_build); free(s->type); free(s->frozen);
     free(s->bond); free(s->angle); free(s->spec_start); free(s->spec);
-    free(s->tab_f); free(s->tab_e); free(s->tab_innersq); free(s->tab_delta);
+    if (!s->tab_shared) { free(s->tab_f); free(s->tab_e); }
+    free(s->tab_innersq); free(s->tab_delta);
     free(s->tab_invdelta); free(s->tab_cut); free(s->nl_start); free(s->nl);
     free(s);
 }
@@ -359,17 +361,37 @@ void esbo_pair_soft(esbo_system *s, double a, const double *cut)
 }
 /* pair_style table lookup N with the effective (I,J) -> table map after replaying the
  * pair_coeff stream (later commands override earlier ones). */
+static void pair_table_common(esbo_system *s, int ntables, int tlm1, const double *f, const double *e,
+                              const double *innersq, const double *delta, const double *cut, const int *tabmap, int shared);
 void esbo_pair_table(esbo_system *s, int ntables, int tlm1, const double *f, const double *e,
                      const double *innersq, const double *delta, const double *cut, const int *tabmap)
 {
-    free(s->tab_f); free(s->tab_e); free(s->tab_innersq); free(s->tab_delta);
+    pair_table_common(s, ntables, tlm1, f, e, innersq, delta, cut, tabmap, 0);
+}
+/* The same, but the (read-only, ~14 MB) LOOKUP arrays stay the caller's: all replicas of a multi-threaded run read ONE
+ * copy, as the threads of one LAMMPS process would.  The caller keeps f and e alive. */
+void esbo_pair_table_shared(esbo_system *s, int ntables, int tlm1, const double *f, const double *e,
+                            const double *innersq, const double *delta, const double *cut, const int *tabmap)
+{
+    pair_table_common(s, ntables, tlm1, f, e, innersq, delta, cut, tabmap, 1);
+}
+static void pair_table_common(esbo_system *s, int ntables, int tlm1, const double *f, const double *e,
+                              const double *innersq, const double *delta, const double *cut, const int *tabmap, int shared)
+{
+    if (!s->tab_shared) { free(s->tab_f); free(s->tab_e); }
+    free(s->tab_innersq); free(s->tab_delta);
     free(s->tab_invdelta); free(s->tab_cut);
     s->pair_mode = 2; s->ntables = ntables; s->tlm1 = tlm1;
     const size_t sz = (size_t)ntables * (size_t)tlm1;
-    s->tab_f = (double *)malloc(sizeof(double) * sz);
-    s->tab_e = (double *)malloc(sizeof(double) * sz);
-    memcpy(s->tab_f, f, sizeof(double) * sz);
-    memcpy(s->tab_e, e, sizeof(double) * sz);
+    s->tab_shared = shared;
+    if (shared) {
+        s->tab_f = (double *)f; s->tab_e = (double *)e;
+    } else {
+        s->tab_f = (double *)malloc(sizeof(double) * sz);
+        s->tab_e = (double *)malloc(sizeof(double) * sz);
+        memcpy(s->tab_f, f, sizeof(double) * sz);
+        memcpy(s->tab_e, e, sizeof(double) * sz);
+    }
     s->tab_innersq = (double *)malloc(sizeof(double) * (size_t)ntables);
     s->tab_delta = (double *)malloc(sizeof(double) * (size_t)ntables);
     s->tab_invdelta = (double *)malloc(sizeof(double) * (size_t)ntables);
@@ -428,11 +450,15 @@ static void build_neighbors(esbo_system *s)
         nb[d] = (int)ceil((s->hi[d] - s->lo[d] + 2.0) / bs);
         if (nb[d] < 1) nb[d] = 1;
     }
+    /* one cell list per atom type, so that atom i searches type tj only as far as cut(ti, tj) + skin reaches
+     * ([LAMMPS-ext] `neighbor multi`: per-type stencils) instead of its largest cutoff for every partner */
     const int nbins = nb[0] * nb[1] * nb[2];
-    int *head = (int *)malloc(sizeof(int) * (size_t)nbins);
+    const int nt1 = s->ntypes + 1;
+    int *head = (int *)malloc(sizeof(int) * (size_t)nbins * (size_t)nt1);
     int *next = (int *)malloc(sizeof(int) * (size_t)n);
     int *bin3 = (int *)malloc(sizeof(int) * (size_t)n * 3);
-    for (int b = 0; b < nbins; b++) head[b] = -1;
+    int pop[ESBO_MAXT] = {0};
+    for (size_t b = 0; b < (size_t)nbins * (size_t)nt1; b++) head[b] = -1;
     for (int i = n - 1; i >= 0; i--) {
         int c[3];
         for (int d = 0; d < 3; d++) {
@@ -442,38 +468,44 @@ static void build_neighbors(esbo_system *s)
             bin3[3 * i + d] = c[d];
         }
         const int b = (c[2] * nb[1] + c[1]) * nb[0] + c[0];
-        next[i] = head[b]; head[b] = i;
+        int *h = head + (size_t)s->type[i] * nbins;
+        next[i] = h[b]; h[b] = i;
+        pop[s->type[i]]++;
     }
+    (void)cutmax_t;
     int cnt = 0;
     for (int i = 0; i < n; i++) {
         s->nl_start[i] = cnt;
         const int ti = s->type[i];
-        const double rmax = cutmax_t[ti] + s->skin;
-        const int rng = (int)ceil(rmax / bs);
         const double xi = s->x[3 * i], yi = s->x[3 * i + 1], zi = s->x[3 * i + 2];
-        for (int cz = bin3[3 * i + 2] - rng; cz <= bin3[3 * i + 2] + rng; cz++) {
-            if (cz < 0 || cz >= nb[2]) continue;
-            for (int cy = bin3[3 * i + 1] - rng; cy <= bin3[3 * i + 1] + rng; cy++) {
-                if (cy < 0 || cy >= nb[1]) continue;
-                for (int cx = bin3[3 * i] - rng; cx <= bin3[3 * i] + rng; cx++) {
-                    if (cx < 0 || cx >= nb[0]) continue;
-                    for (int j = head[(cz * nb[1] + cy) * nb[0] + cx]; j >= 0; j = next[j]) {
-                        if (j <= i) continue;
-                        const double c = pair_cut(s, ti, s->type[j]);
-                        if (c <= 0.0) continue;
-                        const double dx = xi - s->x[3 * j], dy = yi - s->x[3 * j + 1], dz = zi - s->x[3 * j + 2];
-                        const double rsq = dx * dx + dy * dy + dz * dz;
-                        const double cs = c + s->skin;
-                        if (rsq >= cs * cs) continue;
-                        int excluded = 0;
-                        for (int e = s->spec_start[i]; e < s->spec_start[i + 1]; e++)
-                            if (s->spec[e] == j) { excluded = 1; break; }
-                        if (excluded) continue;
-                        if (cnt >= s->nl_cap) {
-                            s->nl_cap = s->nl_cap ? 2 * s->nl_cap : 65536;
-                            s->nl = (int *)realloc(s->nl, sizeof(int) * (size_t)s->nl_cap);
+        for (int tj = 1; tj <= s->ntypes; tj++) {
+            if (!pop[tj]) continue;
+            const double c = pair_cut(s, ti, tj);
+            if (c <= 0.0) continue;
+            const double cs = c + s->skin, cssq = cs * cs;
+            const int rng = (int)ceil(cs / bs);
+            const int *h = head + (size_t)tj * nbins;
+            for (int cz = bin3[3 * i + 2] - rng; cz <= bin3[3 * i + 2] + rng; cz++) {
+                if (cz < 0 || cz >= nb[2]) continue;
+                for (int cy = bin3[3 * i + 1] - rng; cy <= bin3[3 * i + 1] + rng; cy++) {
+                    if (cy < 0 || cy >= nb[1]) continue;
+                    for (int cx = bin3[3 * i] - rng; cx <= bin3[3 * i] + rng; cx++) {
+                        if (cx < 0 || cx >= nb[0]) continue;
+                        for (int j = h[(cz * nb[1] + cy) * nb[0] + cx]; j >= 0; j = next[j]) {
+                            if (j <= i) continue;
+                            const double dx = xi - s->x[3 * j], dy = yi - s->x[3 * j + 1], dz = zi - s->x[3 * j + 2];
+                            const double rsq = dx * dx + dy * dy + dz * dz;
+                            if (rsq >= cssq) continue;
+                            int excluded = 0;
+                            for (int e = s->spec_start[i]; e < s->spec_start[i + 1]; e++)
+                                if (s->spec[e] == j) { excluded = 1; break; }
+                            if (excluded) continue;
+                            if (cnt >= s->nl_cap) {
+                                s->nl_cap = s->nl_cap ? 2 * s->nl_cap : 65536;
+                                s->nl = (int *)realloc(s->nl, sizeof(int) * (size_t)s->nl_cap);
+                            }
+                            s->nl[cnt++] = j;
                         }
-                        s->nl[cnt++] = j;
                     }
                 }
             }
@@ -515,7 +547,9 @@ static int needs_rebuild(esbo_system *s)
 /* Force evaluation.  with_post: apply the post_force fixes (langevin -> walls -> setforce) */
 /* in the order the reference creates them (run_single_shoebox.py:643-671).               */
 /* ------------------------------------------------------------------------------------ */
-static void compute_forces(esbo_system *s, int with_post, int with_noise)
+/* eflag: tally energies (LAMMPS does so only on thermo output steps -- the drivers never set `thermo`, so: at the first and
+ * last step of a run; the parity hook esbo_compute_forces always does) */
+static void compute_forces(esbo_system *s, int with_post, int with_noise, int eflag)
 {
     const int n = s->n;
     double *x = s->x, *f = s->f;
@@ -542,7 +576,7 @@ static void compute_forces(esbo_system *s, int with_post, int with_noise)
                     const double r = sqrt(rsq);
                     const double arg = M_PI * r / c;
                     fpair = (r > 0.0) ? s->soft_a * sin(arg) * M_PI / c / r : 0.0;
-                    e_pair += s->soft_a * (1.0 + cos(arg));
+                    if (eflag) e_pair += s->soft_a * (1.0 + cos(arg));
                 } else {
                     /* [LAMMPS-ext] PairTable::compute, tabstyle LOOKUP */
                     const int t = s->tabmap[ti * ESBO_MAXT + tj];
@@ -552,7 +586,7 @@ static void compute_forces(esbo_system *s, int with_post, int with_noise)
                     int it = (int)((rsq - s->tab_innersq[t]) * s->tab_invdelta[t]);
                     if (it >= s->tlm1) it = s->tlm1 - 1; /* LAMMPS errors out; unreachable for rsq<cut^2 up to rounding */
                     fpair = s->tab_f[(size_t)t * s->tlm1 + it];
-                    e_pair += s->tab_e[(size_t)t * s->tlm1 + it];
+                    if (eflag) e_pair += s->tab_e[(size_t)t * s->tlm1 + it];
                 }
                 s->n_pairs_in_cut++;
                 fxi += dx * fpair; fyi += dy * fpair; fzi += dz * fpair;
@@ -644,7 +678,7 @@ static void compute_forces(esbo_system *s, int with_post, int with_noise)
 int esbo_compute_forces(esbo_system *s, int with_post, int with_noise, double *f_out, double *e_out)
 {
     s->nl_valid = 0;   /* the hook is exact at the current positions: complete list */
-    compute_forces(s, with_post, with_noise);
+    compute_forces(s, with_post, with_noise, 1);
     if (f_out) memcpy(f_out, s->f, sizeof(double) * (size_t)s->n * 3);
     if (e_out) memcpy(e_out, s->energy, sizeof(s->energy));
     return s->status;
@@ -681,7 +715,7 @@ int esbo_run(esbo_system *s, int nsteps, long long start_step, long long stop_st
     const double dtv = s->dt, dtf = 0.5 * s->dt;
     s->nl_valid = 0; /* setup always rebuilds */
     apply_adapt(s, rb, re, 1);
-    compute_forces(s, 1, 1);
+    compute_forces(s, 1, 1, 1);
     for (int it = 0; it < nsteps && s->status == 0; it++) {
         s->step++;
         for (int i = 0; i < 3 * n; i++) {
@@ -690,7 +724,7 @@ int esbo_run(esbo_system *s, int nsteps, long long start_step, long long stop_st
         }
         /* [LAMMPS-ext] boundary f f f: an atom outside the box at re-neighbouring is lost */
         apply_adapt(s, rb, re, 0);
-        compute_forces(s, 1, 1);
+        compute_forces(s, 1, 1, 0);
         for (int i = 0; i < 3 * n; i++) s->v[i] += dtf * s->f[i];
     }
     for (int i = 0; i < n && s->status == 0; i++)

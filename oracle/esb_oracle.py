@@ -33,7 +33,8 @@ def build_native() -> str:
     src = os.path.join(_HERE, "esb_oracle.c")
     out = os.path.join(_HERE, "libesb_oracle_native.so")
     if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src) or os.environ.get("ESB_ORACLE_REBUILD"):
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-fno-fast-math", "-ffp-contract=off", "-fPIC", "-shared",
+        # timing build: what a stock -O3 -march=native LAMMPS build gets (FMA contraction allowed); never used for parity
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fno-fast-math", "-ffp-contract=fast", "-fPIC", "-shared",
                                "-o", out, src, "-lm"])
     _LIB_PATH, _lib = out, None
     return out
@@ -69,6 +70,7 @@ def lib():
         L.esbo_set_neigh_delay.argtypes = [vp, C.c_int]
         L.esbo_pair_soft.argtypes = [vp, C.c_double, dp]
         L.esbo_pair_table.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, dp, ip]
+        L.esbo_pair_table_shared.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, dp, ip]
         L.esbo_pair_table_remap.argtypes = [vp, ip]
         L.esbo_clear_adapt.argtypes = [vp]
         L.esbo_add_adapt.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
@@ -124,10 +126,13 @@ def build_lookup_table(section, cut: float, tablength: int = 30000):
     return e, f, float(prm[0]), float(prm[1])
 
 
+_shared_arrays: dict = {}
+
+
 class Oracle:
     """One replica on the CPU, driven chunk by chunk with the reference's command stream."""
 
-    def __init__(self, data, tables=None, lookup=None, seed: int = 1, skin: float = 0.3, neigh_delay: int = 10):
+    def __init__(self, data, tables=None, lookup=None, seed: int = 1, skin: float = 0.3, neigh_delay: int = 10, shared_tables: bool = False):
         """`data`: ShoeboxData.  `tables`: protocol.PairTables.  `lookup`: list of (e, f, innersq, delta)
         per table spec (see `build_lookup_table`)."""
         from enhancershoebox_b200 import protocol as P
@@ -156,6 +161,7 @@ class Oracle:
         self.L.esbo_set_neigh_delay(self.h, neigh_delay)          # neigh_modify every 1 delay 10 check yes (:533)
         self.tables = tables
         self.lookup = lookup
+        self.shared_tables = shared_tables          # one copy of the LOOKUP arrays for all replicas of a multi-threaded run
         self._pair = None
         self.soft_cut = np.ascontiguousarray(P.soft_cutoffs(), np.float64)
 
@@ -187,7 +193,14 @@ class Oracle:
                 inner = np.array([l[2] for l in self.lookup])
                 delta = np.array([l[3] for l in self.lookup])
                 cut = np.array([c for (_, c) in self.tables.specs], np.float64)
-                self.L.esbo_pair_table(self.h, nt, tlm1, _dp(f), _dp(e), _dp(inner), _dp(delta), _dp(cut), _ip(tm))
+                if self.shared_tables:
+                    key = id(self.lookup)
+                    if key not in _shared_arrays:
+                        _shared_arrays[key] = (self.lookup, f, e)          # kept alive for every replica that points at them
+                    _, f, e = _shared_arrays[key]
+                    self.L.esbo_pair_table_shared(self.h, nt, tlm1, _dp(f), _dp(e), _dp(inner), _dp(delta), _dp(cut), _ip(tm))
+                else:
+                    self.L.esbo_pair_table(self.h, nt, tlm1, _dp(f), _dp(e), _dp(inner), _dp(delta), _dp(cut), _ip(tm))
             else:
                 self.L.esbo_pair_table_remap(self.h, _ip(tm))
         self._pair = pair

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("-t", "--total", type=int, default=None, help="Python timesteps per run (default 2000)")
     ap.add_argument("--batch-groups", type=int, default=118, help="5-run groups per batch (118 x 5 = 590 replicas = two CTAs per SM)")
     ap.add_argument("-o", "--out", default="summary_contact_grouped_Thresholds10-100.txt")
+    ap.add_argument("--cpp", action="store_true", help="write the table in the format of dist_genestages_grouped_cpp (no index column, 6 significant digits)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -38,7 +39,7 @@ def main():
         if (dist.get_rank() if dist.is_initialized() else 0) == 0:
             out = args.out if len(args.box) == 1 else f"{args.out}.box{box}"
             with open(out, "w") as f:
-                f.write(sweep.summary_csv(groups, rows))
+                f.write(sweep.summary_cpp_csv(groups, rows) if args.cpp else sweep.summary_csv(groups, rows))
             print(f"box {box}: {len(groups)} rows -> {out} in {time.time() - t0:.1f} s")
     if dist.is_initialized():
         dist.destroy_process_group()

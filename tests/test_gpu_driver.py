@@ -72,3 +72,21 @@ def test_failed_repeat_is_rerun_with_a_new_seed(tmp_path, monkeypatch):
     for r in (1, 2, 3):
         assert os.path.exists(os.path.join("out", f"run{r}", "figures", "ser5p_cluster.pdf"))
         assert len(open(os.path.join("out", f"run{r}", "geneTrack.txt")).read().splitlines()) == 12
+
+
+def test_run_refuses_a_chunk_whose_pair_setup_was_never_given(box11):
+    """A schedule that names table map "T" (treatment) on a Control batch, for which only maps A and B were uploaded:
+    esb_run must fail (ESB_ESTATE) instead of stepping without pair forces."""
+    from enhancershoebox_b200 import engine as E, protocol as P
+    eng = E.ShoeboxBatch(box11, n_replicas=2, seeds=[1, 2])
+    plans = [P.ChunkPlan(p.index, "T", p.ramp, p.adapt_soft, p.adapt_bond1, p.adapt_bond2, 5) for p in P.chunk_schedule("genes_stages", n_chunks=22)[20:]]
+    eng.set_schedule(plans=plans, observe=False)
+    with pytest.raises(E.EsbError, match="-4"):
+        eng.run()
+    eng.close()
+
+
+def test_unchanged_launcher_spreads_over_the_gpus():
+    from enhancershoebox_b200 import drivers
+    assert [drivers.pick_device([r], 8) for r in (1, 2, 8, 9, 100)] == [1, 2, 0, 1, 4]
+    assert drivers.pick_device([5], 1) == 0

@@ -1,6 +1,7 @@
 """Level 3: ensemble statistics of the device path against the fp64 oracle (statistical parity).
 
-Reference ensemble: tests/golden/oracle_ensemble_box11.npz = 48 oracle replicas x 400 chunks
+Reference ensembles: tests/golden/oracle_ensemble_box11.npz = 48 oracle replicas x 400 chunks and
+oracle_ensemble_box11_2000.npz = 48 x 2000 chunks, the production run length
 (box 11, promoter 3, -x 20, -a 100; made by tests/golden/make_oracle_ensemble.py).  The device runs
 192 replicas of the same protocol with different seeds.  Window means must agree within 4.5
 standard errors of the difference (both ensembles contribute); quantities fixed by the protocol
@@ -15,14 +16,18 @@ from enhancershoebox_b200 import datafile, engine as E
 
 pytestmark = pytest.mark.gpu
 WINDOWS = ((20, 100), (100, 200), (200, 300), (300, 400))
+WINDOWS_FULL = ((20, 150), (150, 400), (400, 800), (800, 1200), (1200, 1600), (1600, 2000))
 
 
 def _sem_diff(a, b):
     return np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
 
 
-def test_ensemble_matches_oracle():
-    z = np.load(os.path.join(GOLDEN, "oracle_ensemble_box11.npz"))
+@pytest.mark.parametrize("fixture,windows", [("oracle_ensemble_box11.npz", WINDOWS), ("oracle_ensemble_box11_2000.npz", WINDOWS_FULL)])
+def test_ensemble_matches_oracle(fixture, windows):
+    """400 chunks (12 % RNP at the end) and the production run length, 2000 chunks x 200 steps (90 % RNP, where the
+    cut-2.9 RNP-RNP attraction dominates): fp32 state on the device over 4e5 steps against the fp64 oracle."""
+    z = np.load(os.path.join(GOLDEN, fixture))
     nch, thr, act = [int(v) for v in z["meta"]]
     R = 192
     datas = [datafile.make_shoebox(11, 3, False, seed=10_000 + r) for r in range(R)]
@@ -40,7 +45,7 @@ def test_ensemble_matches_oracle():
     ke = 0.5 * (v ** 2).sum(axis=(1, 2)) / x.shape[1]
     assert abs(ke.mean() - z["ke"][:, 20:].mean()) < 0.02
     report = []
-    for lo, hi in WINDOWS:
+    for lo, hi in windows:
         for name, col in (("d_rp", 4), ("d_rg", 5), ("n_prom", 6), ("n_gene", 7)):
             g = fr[:, lo:hi, col].mean(axis=1)
             o = z[name][:, lo:hi].astype(np.float64).mean(axis=1)

@@ -10,11 +10,17 @@ from oracle import observe as OB
 pytestmark = pytest.mark.gpu
 
 
-def test_frames_bit_exact_chunk_by_chunk(box11, snapshots):
+@pytest.mark.parametrize("promoter", [3, 2, 1])
+def test_frames_bit_exact_chunk_by_chunk(snapshots, promoter):
+    """Promoter lengths 1 and 2 exercise the probe-index quirk of run_single_shoebox.py:941 (the "promoter probe" is
+    atom g - p + 1: the last promoter bead for p = 3, the gene start bead for p = 2, the second gene bead for p = 1)
+    and the p-bead promoter mean of d_rp (:946) on the device."""
+    from enhancershoebox_b200 import datafile
+    box11 = datafile.make_shoebox(11, promoter, False, seed=7)
     R = 4
-    x0 = snapshots["x500"].astype(np.float64)
+    x0 = snapshots["x500"].astype(np.float64)                      # (an equilibrated promoter-3 frame: same bead count and chain layout)
     v0 = snapshots["v500"].astype(np.float64)
-    t0 = snapshots["t20"].astype(np.int32)                         # all RBP, gene inactive
+    t0 = np.asarray(box11.types, np.int32).copy()                  # all RBP, gene inactive, promoter of this length
     seeds = [11, 12, 13, 14]
     thr, act = [5, 5, 1000, 5], [1000, 300, 1000, 0]              # always / sometimes / never (count) / never (p = 0)
     eng = E.ShoeboxBatch(box11, n_replicas=R, seeds=seeds, thresholds=thr, activations=act)
@@ -40,8 +46,11 @@ def test_frames_bit_exact_chunk_by_chunk(box11, snapshots):
             assert np.array_equal(t[r], types[r]), (pl.index, r)
             assert list(hist[r, 0]) == OB.shell_histogram(x[r], lay, P.CLUSTER_R)
             seen_states.add((r, s))
-    assert {(0, 1), (0, 2), (2, 1), (3, 1)} <= seen_states and (2, 2) not in seen_states and (3, 2) not in seen_states
-    assert eng.counters()["total_active"][0] == machines[0].total_active > 0
+    assert {(0, 1), (2, 1), (3, 1)} <= seen_states and (2, 2) not in seen_states and (3, 2) not in seen_states
+    if promoter == 3:
+        assert (0, 2) in seen_states
+    assert eng.counters()["total_active"][0] == machines[0].total_active
+    assert lay.probe == box11.gene_start() - promoter + 1
     assert np.all(eng.status() == 0)
     eng.close()
 
