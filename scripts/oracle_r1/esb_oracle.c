@@ -187,7 +187,6 @@ typedef struct esbo_system {
     double soft_a, soft_cut[ESBO_MAXT * ESBO_MAXT];
     int ntables, tlm1;
     double *tab_f, *tab_e, *tab_innersq, *tab_delta, *tab_invdelta, *tab_cut;
-    int tab_shared;            /* tab_f / tab_e belong to the caller */
     int tabmap[ESBO_MAXT * ESBO_MAXT];
     /* adapt */
     int nadapt;
@@ -233,8 +232,7 @@ void esbo_destroy(esbo_system *s)
     if (!s) return;
     free(s->x); free(s->v); free(s->f); free(s->x_build); free(s->type); free(s->frozen);
     free(s->bond); free(s->angle); free(s->spec_start); free(s->spec);
-    if (!s->tab_shared) { free(s->tab_f); free(s->tab_e); }
-    free(s->tab_innersq); free(s->tab_delta);
+    free(s->tab_f); free(s->tab_e); free(s->tab_innersq); free(s->tab_delta);
     free(s->tab_invdelta); free(s->tab_cut); free(s->nl_start); free(s->nl);
     free(s);
 }
@@ -361,37 +359,17 @@ void esbo_pair_soft(esbo_system *s, double a, const double *cut)
 }
 /* pair_style table lookup N with the effective (I,J) -> table map after replaying the
  * pair_coeff stream (later commands override earlier ones). */
-static void pair_table_common(esbo_system *s, int ntables, int tlm1, const double *f, const double *e,
-                              const double *innersq, const double *delta, const double *cut, const int *tabmap, int shared);
 void esbo_pair_table(esbo_system *s, int ntables, int tlm1, const double *f, const double *e,
                      const double *innersq, const double *delta, const double *cut, const int *tabmap)
 {
-    pair_table_common(s, ntables, tlm1, f, e, innersq, delta, cut, tabmap, 0);
-}
-/* The same, but the (read-only, ~14 MB) LOOKUP arrays stay the caller's: all replicas of a multi-threaded run read ONE
- * copy, as the threads of one LAMMPS process would.  The caller keeps f and e alive. */
-void esbo_pair_table_shared(esbo_system *s, int ntables, int tlm1, const double *f, const double *e,
-                            const double *innersq, const double *delta, const double *cut, const int *tabmap)
-{
-    pair_table_common(s, ntables, tlm1, f, e, innersq, delta, cut, tabmap, 1);
-}
-static void pair_table_common(esbo_system *s, int ntables, int tlm1, const double *f, const double *e,
-                              const double *innersq, const double *delta, const double *cut, const int *tabmap, int shared)
-{
-    if (!s->tab_shared) { free(s->tab_f); free(s->tab_e); }
-    free(s->tab_innersq); free(s->tab_delta);
+    free(s->tab_f); free(s->tab_e); free(s->tab_innersq); free(s->tab_delta);
     free(s->tab_invdelta); free(s->tab_cut);
     s->pair_mode = 2; s->ntables = ntables; s->tlm1 = tlm1;
     const size_t sz = (size_t)ntables * (size_t)tlm1;
-    s->tab_shared = shared;
-    if (shared) {
-        s->tab_f = (double *)f; s->tab_e = (double *)e;
-    } else {
-        s->tab_f = (double *)malloc(sizeof(double) * sz);
-        s->tab_e = (double *)malloc(sizeof(double) * sz);
-        memcpy(s->tab_f, f, sizeof(double) * sz);
-        memcpy(s->tab_e, e, sizeof(double) * sz);
-    }
+    s->tab_f = (double *)malloc(sizeof(double) * sz);
+    s->tab_e = (double *)malloc(sizeof(double) * sz);
+    memcpy(s->tab_f, f, sizeof(double) * sz);
+    memcpy(s->tab_e, e, sizeof(double) * sz);
     s->tab_innersq = (double *)malloc(sizeof(double) * (size_t)ntables);
     s->tab_delta = (double *)malloc(sizeof(double) * (size_t)ntables);
     s->tab_invdelta = (double *)malloc(sizeof(double) * (size_t)ntables);
@@ -537,9 +515,7 @@ static int needs_rebuild(esbo_system *s)
 /* Force evaluation.  with_post: apply the post_force fixes (langevin -> walls -> setforce) */
 /* in the order the reference creates them (run_single_shoebox.py:643-671).               */
 /* ------------------------------------------------------------------------------------ */
-/* eflag: tally energies (LAMMPS does so only on thermo output steps -- the drivers never set `thermo`, so: at the first and
- * last step of a run; the parity hook esbo_compute_forces always does) */
-static void compute_forces(esbo_system *s, int with_post, int with_noise, int eflag)
+static void compute_forces(esbo_system *s, int with_post, int with_noise)
 {
     const int n = s->n;
     double *x = s->x, *f = s->f;
@@ -566,7 +542,7 @@ static void compute_forces(esbo_system *s, int with_post, int with_noise, int ef
                     const double r = sqrt(rsq);
                     const double arg = M_PI * r / c;
                     fpair = (r > 0.0) ? s->soft_a * sin(arg) * M_PI / c / r : 0.0;
-                    if (eflag) e_pair += s->soft_a * (1.0 + cos(arg));
+                    e_pair += s->soft_a * (1.0 + cos(arg));
                 } else {
                     /* [LAMMPS-ext] PairTable::compute, tabstyle LOOKUP */
                     const int t = s->tabmap[ti * ESBO_MAXT + tj];
@@ -576,7 +552,7 @@ static void compute_forces(esbo_system *s, int with_post, int with_noise, int ef
                     int it = (int)((rsq - s->tab_innersq[t]) * s->tab_invdelta[t]);
                     if (it >= s->tlm1) it = s->tlm1 - 1; /* LAMMPS errors out; unreachable for rsq<cut^2 up to rounding */
                     fpair = s->tab_f[(size_t)t * s->tlm1 + it];
-                    if (eflag) e_pair += s->tab_e[(size_t)t * s->tlm1 + it];
+                    e_pair += s->tab_e[(size_t)t * s->tlm1 + it];
                 }
                 s->n_pairs_in_cut++;
                 fxi += dx * fpair; fyi += dy * fpair; fzi += dz * fpair;
@@ -668,7 +644,7 @@ static void compute_forces(esbo_system *s, int with_post, int with_noise, int ef
 int esbo_compute_forces(esbo_system *s, int with_post, int with_noise, double *f_out, double *e_out)
 {
     s->nl_valid = 0;   /* the hook is exact at the current positions: complete list */
-    compute_forces(s, with_post, with_noise, 1);
+    compute_forces(s, with_post, with_noise);
     if (f_out) memcpy(f_out, s->f, sizeof(double) * (size_t)s->n * 3);
     if (e_out) memcpy(e_out, s->energy, sizeof(s->energy));
     return s->status;
@@ -705,7 +681,7 @@ int esbo_run(esbo_system *s, int nsteps, long long start_step, long long stop_st
     const double dtv = s->dt, dtf = 0.5 * s->dt;
     s->nl_valid = 0; /* setup always rebuilds */
     apply_adapt(s, rb, re, 1);
-    compute_forces(s, 1, 1, 1);
+    compute_forces(s, 1, 1);
     for (int it = 0; it < nsteps && s->status == 0; it++) {
         s->step++;
         for (int i = 0; i < 3 * n; i++) {
@@ -714,7 +690,7 @@ int esbo_run(esbo_system *s, int nsteps, long long start_step, long long stop_st
         }
         /* [LAMMPS-ext] boundary f f f: an atom outside the box at re-neighbouring is lost */
         apply_adapt(s, rb, re, 0);
-        compute_forces(s, 1, 1, 0);
+        compute_forces(s, 1, 1);
         for (int i = 0; i < 3 * n; i++) s->v[i] += dtf * s->f[i];
     }
     for (int i = 0; i < n && s->status == 0; i++)

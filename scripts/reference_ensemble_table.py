@@ -24,5 +24,10 @@ if "--summary" in sys.argv:
     for k, v in by.items():
         v = np.array(v)
         print(f"| {k} | {len(v)} | {v.mean():+.3f} | {np.sqrt((v ** 2).mean()):.3f} | {np.abs(v).max():.2f} |")
+    cells, _ = EC.load_golden()
+    print("\n| promoter | quantity | device mean over cells +- se | reference mean over cells +- se | z |\n|---|---|---|---|---|")
+    for p, rows in EC.promoter_means(res, cells).items():
+        for name, dm, dse, rm, rse, z in rows:
+            print(f"| {p} | {name} | {dm:.2f} +- {dse:.2f} | {rm:.2f} +- {rse:.2f} | {z:+.2f} |")
 else:
     print(EC.table(comp))

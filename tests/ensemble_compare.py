@@ -70,3 +70,24 @@ def table(comparisons) -> str:
         for name, m1, s1, n1, m2, s2, n2, z in comp:
             lines.append(f"| ({cell}) | {name} | {m1:.3f} ± {s1:.3f} ({n1}) | {m2:.3f} ± {s2:.3f} ({n2}) | {z:+.2f} |")
     return "\n".join(lines)
+
+
+def promoter_means(res, cells):
+    """Mean over the cells of one promoter length of the cell means of S5PInt, S2PInt, Contact -- the rows of BASELINE.md's
+    "mean over all cells, by promoter" -- for the device result `res` and the reference, with the standard error of each
+    (cells are independent ensembles) and z of the difference.  {promoter: [(name, dev, dev_se, ref, ref_se, z)]}"""
+    out = {}
+    for p in (1, 2, 3):
+        dev = [_arr(v) for k, v in res["cells"].items() if k.startswith(f"{p},")]
+        ref = [cells[tuple(int(q) for q in k.split(","))] for k in res["cells"] if k.startswith(f"{p},")]
+        if not dev:
+            continue
+        rows = []
+        for c, key in ((0, "s5p"), (1, "s2p"), (2, "contact")):
+            dm = float(np.mean([d[:, c].mean() for d in dev]))
+            rm = float(np.mean([r[key][0] for r in ref]))
+            dse = float(np.sqrt(sum(d[:, c].var(ddof=1) / len(d) for d in dev)) / len(dev))
+            rse = float(np.sqrt(sum(r[key][1] ** 2 / r["n"] for r in ref)) / len(ref))
+            rows.append((COLUMNS[c], dm, dse, rm, rse, (dm - rm) / float(np.hypot(dse, rse))))
+        out[p] = rows
+    return out

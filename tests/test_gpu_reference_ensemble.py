@@ -5,8 +5,11 @@ The device runs the PRODUCTION protocol -- box 11, fresh make_input_file initial
 switch, 2000 Python timesteps x 200 MD steps, gene state machine, RBP->RNP ramp to 90 % -- 100 repeats per cell for
 the five quoted cells and compares S5PInt, S2PInt, Contact, DistActivation (mean over repeats; DistActivation over the
 activating repeats) and the fraction of activating repeats with the 100 LAMMPS repeats of the same cell.
-Stated tolerance: |z| < 4 per comparison (both samples' standard errors), sum of z^2 over the 25 comparisons < 60
-(chi^2_25: p = 1e-4), S2PInt a whole number of frames out of 1850."""
+Stated tolerance: |z| < 4 per comparison (both samples' standard errors); S5PInt, S2PInt, Contact and the activating
+fraction of one cell move together (all four follow whether the Ser5P cluster sits at the gene), so the joint statistic
+takes two weakly correlated quantities per cell: sum over the five cells of z(S5PInt)^2 + z(DistActivation)^2 < 35.6
+(chi^2_10: p = 1e-4); S2PInt a whole number of frames out of 1850.  The 330-cell sweep (profiles/
+r2_reference_ensemble_all.md, checked by tests/test_reference_ensemble.py) is the test of systematic deviations."""
 import numpy as np
 import pytest
 
@@ -20,7 +23,7 @@ REPEATS = 100
 
 def test_production_ensembles_match_the_reference_tables():
     cells, _ = EC.load_golden()
-    zs, report = [], {}
+    zs, joint, report = [], [], {}
     for p in (1, 2, 3):
         runs = [(c, k) for c in QUOTED if c[0] == p for k in range(REPEATS)]
         seeds = np.array([31_000_000 + 1000 * (c[1] * 1000 + c[2]) + k for c, k in runs], dtype=np.uint64)
@@ -40,7 +43,8 @@ def test_production_ensembles_match_the_reference_tables():
             report[",".join(map(str, c))] = comp
             assert EC.s2p_is_quantised(rows[sel])
             zs += [q[-1] for q in comp]
+            joint += [q[-1] for q in comp if q[0] in ("S5PInt", "DistActivation")]
     print(EC.table(report))
-    zs = np.array(zs)
+    zs, joint = np.array(zs), np.array(joint)
     assert np.all(np.abs(zs) < 4.0), EC.table(report)
-    assert float((zs ** 2).sum()) < 60.0, EC.table(report)
+    assert float((joint ** 2).sum()) < 35.6, EC.table(report)

@@ -26,12 +26,23 @@ def test_golden_table_known_answers():
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_reference_ensemble_*.json"))))
 def test_committed_device_ensembles_match_the_reference(path):
+    """Stated tolerances.  Cells with the reference's own 100 repeats: |z| < 4 per comparison.  The 330-cell sweep at 20
+    repeats per cell (heavy-tailed per-run distributions, small samples): |z| < 6.5, at most 3 % of the comparisons beyond
+    3, mean z over all comparisons within 0.15 of zero, and the per-promoter means of S5PInt, S2PInt and Contact
+    (BASELINE.md's last row) within 3.5 combined standard errors of the reference's."""
     comp, res = EC.compare_result_file(path)
+    cells, _ = EC.load_golden()
     assert res["chunks"] == 2000 and res["box"] == 11
     n_runs = sum(len(v) for v in res["cells"].values())
     assert res["failed"] <= 0.03 * (n_runs + res["failed"])
     zs = np.array([q[-1] for c in comp.values() for q in c if np.isfinite(q[-1])])
-    # per comparison |z| < 4 when the cell has the reference's 100 repeats; sweeps with fewer repeats per cell are
-    # judged on the distribution of z over all cells: mean ~ 0, rms ~ 1
-    assert np.all(np.abs(zs) < 4.5), EC.table(comp)
-    assert abs(zs.mean()) < 4.0 / np.sqrt(len(zs)) + 0.05 and 0.5 < zs.std() < 1.5, (zs.mean(), zs.std())
+    if res["repeats"] >= 100:
+        assert np.all(np.abs(zs) < 4.0), EC.table(comp)
+    else:
+        assert np.all(np.abs(zs) < 6.5) and np.mean(np.abs(zs) > 3.0) < 0.03, (np.abs(zs).max(), np.mean(np.abs(zs) > 3.0))
+    assert abs(zs.mean()) < 0.15 + 4.0 / np.sqrt(len(zs)) and 0.5 < zs.std() < 1.5, (zs.mean(), zs.std())
+    if len(comp) == 330:
+        pm = EC.promoter_means(res, cells)
+        for p, rows in pm.items():
+            for name, dm, dse, rm, rse, z in rows:
+                assert abs(z) < 3.5 and abs(dm / rm - 1.0) < 0.15, (p, name, dm, rm, z)
