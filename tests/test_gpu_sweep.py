@@ -26,3 +26,23 @@ def test_sweep_rows_equal_host_aggregation_of_the_same_runs():
     assert np.all(rows[:, 0] >= 0) and np.all((rows[:, 2] >= 0) & (rows[:, 2] <= 100))
     csv = sweep.summary_csv(groups, rows)
     assert len(csv.splitlines()) == 5
+
+
+def test_run_sweep_two_ranks_nccl(tmp_path):
+    """run_sweep.py as its own docstring launches it -- torchrun, one rank per GPU, process group "nccl" -- on two GPUs:
+    the end-of-run all_gather of the per-group rows must move DEVICE tensors (a CPU tensor has no NCCL backend) and the
+    table must equal the one-rank table row for row.  Skipped where fewer than two GPUs are visible."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    common = ["-b", "9", "--promoters", "3", "2", "--activations", "100", "--thresholds", "10", "20", "--repeats", "5", "-t", "170", "--batch-groups", "2"]
+    one = os.path.join(tmp_path, "one.txt")
+    two = os.path.join(tmp_path, "two.txt")
+    subprocess.check_call([sys.executable, os.path.join(root, "run_sweep.py"), *common, "-o", one], cwd=root)
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                           "--master-port", "29611", os.path.join(root, "run_sweep.py"), *common, "-o", two], cwd=root)
+    assert open(one).read() == open(two).read() and len(open(two).read().splitlines()) == 5
