@@ -1235,7 +1235,7 @@ __device__ __noinline__ void voxel_counts(const KArgs &a, const int r, const int
 // ------------------------------------------------------------------------------------------------
 // Actin events between two `run` commands (run_single_shoebox.py:969-1298): nucleation of two free
 // monomers, polymerisation at the plus end (every chunk) and at the minus end (every 40th),
-// depolymerisation at the minus end (every 5th), each with the relocation of the moved monomer by
+// depolymerisation at the minus end (every 5th) and at the plus end (i % 4000 == 0), each with the relocation of the moved monomer by
 // rejection sampling (`set atom ID x y z`), followed by what `create_bonds single/bond 2`,
 // `single/angle 2` and `delete_bonds ... remove special` do to the topology.  Filaments are linear, so the
 // whole topology of the actin beads is two links per bead (neighbour towards the plus / minus end) from
@@ -1402,6 +1402,33 @@ __device__ __noinline__ void actin_events(const KArgs &a, const int r, const esb
                 }
                 if (!(n_tries > a.act.max_tries)) place(curr, q);
                 if (lp(nxt) == (int)ESB_NOLINK) {                            // a filament of length 1 is no filament (:1196-1203)
+                    fr[nfree++] = (unsigned short)nxt;
+                    fplus[j] = ESB_NOLINK;
+                }
+            }
+            int w = 0;
+            for (int j = 0; j < nfil; j++) if (fplus[j] != ESB_NOLINK) { fplus[w] = fplus[j]; fminus[w] = fminus[j]; w++; }
+            nfil = w;
+        }
+        // ---------------- depolymerisation at the plus end (:1220-1250; i % t_off_plus == 0) ----------------
+        if (d.actin_flags & 8) {
+            for (int j = 0; j < nfil; j++) {
+                const int curr = fplus[j], nxt = lm(curr);
+                link[curr - first] = 0xffffffffu;
+                set_lp(nxt, ESB_NOLINK);
+                fr[nfree++] = (unsigned short)curr;
+                fplus[j] = (unsigned short)nxt;
+                const D3 c = d3_of(S.pos[curr]), cn = d3_of(S.pos[nxt]);
+                int n_tries = 0;
+                D3 q;
+                for (;;) {
+                    n_tries++;
+                    q = sample(c, a.act.free_box);
+                    if (d3_dist(cn, q) > a.act.free_min) break;
+                    if (n_tries > a.act.max_tries) break;
+                }
+                if (!(n_tries > a.act.max_tries)) place(curr, q);
+                if (lm(nxt) == (int)ESB_NOLINK) {                            // a filament of length 1 is no filament (:1245-1248)
                     fr[nfree++] = (unsigned short)nxt;
                     fplus[j] = ESB_NOLINK;
                 }

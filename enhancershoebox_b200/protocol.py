@@ -59,6 +59,7 @@ T_POLYMERIZATION_ON = 40
 T_ON_PLUS = 1
 T_ON_MINUS = 40
 T_OFF_MINUS = 5
+T_OFF_PLUS = 2 * N_RUNS                 # run_single_shoebox.py:496
 P_ON = 0.3
 SIG_ACTIN = 0.3
 W_SA = 0.2
@@ -69,10 +70,13 @@ STATIC_ACTIN_CONDITIONS = ("LatB", "SwinA_nopol")            # t_polymerization_
 
 def actin_flags(i: int, condition: str = "Control") -> int:
     """Which actin events Python timestep i performs (run_single_shoebox.py:969, 1064, 1101, 1168):
-    1 = nucleation + plus-end polymerisation, 2 = minus-end polymerisation, 4 = minus-end depolymerisation."""
+    1 = nucleation + plus-end polymerisation, 2 = minus-end polymerisation, 4 = minus-end depolymerisation,
+    8 = plus-end depolymerisation (i % t_off_plus == 0 with t_off_plus = 2 NRuns, :496, 1220-1250: once, at i = 4000, in
+    the 5000-chunk JQ-1 / Flavopiridol runs)."""
     if condition in STATIC_ACTIN_CONDITIONS or (i + 1) < T_POLYMERIZATION_ON:
         return 0
-    return 1 | (2 if i % (T_ON_PLUS * T_ON_MINUS) == 0 else 0) | (4 if i % T_OFF_MINUS == 0 else 0)
+    return (1 | (2 if i % (T_ON_PLUS * T_ON_MINUS) == 0 else 0) | (4 if i % T_OFF_MINUS == 0 else 0)
+            | (8 if i % T_OFF_PLUS == 0 else 0))
 
 
 # synthetic microscopy (run_single_shoebox.py:152-213, 1498-1502)

@@ -77,7 +77,8 @@ typedef struct {
                              * ((i+1) % 10 == 0 and make_microscopy, run_single_shoebox.py:1498-1502) */
     int actin_flags;        /* actin events of this chunk (run_single_shoebox.py:969-1298): 1 = nucleation + plus-end
                              * polymerisation ((i+1) >= t_polymerization_on), 2 = minus-end polymerisation
-                             * (i % (t_on_plus*t_on_minus) == 0), 4 = minus-end depolymerisation (i % t_off_minus == 0) */
+                             * (i % (t_on_plus*t_on_minus) == 0), 4 = minus-end depolymerisation (i % t_off_minus == 0),
+                             * 8 = plus-end depolymerisation (i % t_off_plus == 0, t_off_plus = 2 NRuns: :496, 1220-1250) */
 } esb_chunk_desc;
 
 /* Actin polymerisation dynamics (run_single_shoebox.py:398-423, 489-496, 969-1298).  Actin beads are the atoms

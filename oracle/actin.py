@@ -1,7 +1,7 @@
 """Restatement of the reference's actin events (TEST INFRASTRUCTURE, see esb_oracle.c).
 
 Follows ``run_single_shoebox.py:969-1298`` statement by statement -- nucleation (:973-1038), plus/minus-end
-polymerisation (:1062-1135), minus-end depolymerisation (:1168-1214) with the reference's own list
+polymerisation (:1062-1135), minus-end (:1168-1214) and plus-end (:1220-1250) depolymerisation with the reference's own list
 bookkeeping (``free_actin``, ``filament_details``) -- with two substitutions, both shared with the device
 (enhancershoebox_b200/csrc/esb_kernels.cu, actin_events):
 
@@ -28,6 +28,7 @@ P_ON = 0.3
 T_ON_PLUS = 1
 T_ON_MINUS = 40
 T_OFF_MINUS = 5
+T_OFF_PLUS = 4000                       # 2 * NRuns (run_single_shoebox.py:496)
 MAX_TRIES = 2000
 
 
@@ -164,6 +165,31 @@ class ActinState:
                     place(curr_atom, new_loc)
                 if len(filament_details[j]) < 2:
                     free_actin.append(filament_details[j][0])
+            for j in sorted([j for j in range(len(filament_details)) if len(filament_details[j]) < 2], reverse=True):
+                del filament_details[j]
+        # ---- depolymerisation at the plus end (:1220-1250; i % t_off_plus == 0, t_off_plus = 2 NRuns) ----
+        if i % T_OFF_PLUS == 0:
+            assert flags & 8
+            for f in filament_details:
+                self._delete_touching(f[0])
+            for j in range(len(filament_details)):
+                curr_atom = filament_details[j][0]
+                next_atom = filament_details[j][1]
+                free_actin.append(curr_atom)
+                filament_details[j].remove(curr_atom)
+                n_tries = 0
+                while 1:
+                    n_tries = n_tries + 1
+                    new_loc = uniform(pos(curr_atom), 1.0)
+                    d = dist(pos(next_atom), new_loc)
+                    if d > SIG_ACTIN:
+                        break
+                    if n_tries > MAX_TRIES:
+                        break
+                if not n_tries > MAX_TRIES:
+                    place(curr_atom, new_loc)
+                if len(filament_details[j]) < 2:
+                    free_actin.append(filament_details[j][-1])
             for j in sorted([j for j in range(len(filament_details)) if len(filament_details[j]) < 2], reverse=True):
                 del filament_details[j]
         return m[0]

@@ -31,10 +31,13 @@ def main():
     ap.add_argument("--box", type=int, default=11)
     ap.add_argument("--batch", type=int, default=592)
     ap.add_argument("--seed-base", type=int, default=7_000_000)
+    ap.add_argument("--ic", default="fresh", choices=["fresh", "bundled"],
+                    help="fresh: a new make_input_file configuration per repeat; bundled: every repeat starts from the reference's one "
+                         "bundled data file of that promoter length, as the reference's launcher does (tests/golden/bundled_ic_bs11.npz)")
     ap.add_argument("--out", default="gpurun_out/ref_ensemble.json")
     args = ap.parse_args()
     cells = QUOTED if args.cells == "quoted" else [(p, t, a) for p in (1, 2, 3) for a in ACTIVATIONS for t in THRESHOLDS]
-    res = {"box": args.box, "chunks": args.chunks, "repeats": args.repeats, "cells": {}, "failed": 0}
+    res = {"box": args.box, "chunks": args.chunks, "repeats": args.repeats, "ic": args.ic, "cells": {}, "failed": 0}
     t_all = time.time()
     steps = 0
     for p in (1, 2, 3):
@@ -42,8 +45,14 @@ def main():
         for lo in range(0, len(runs), args.batch):
             part = runs[lo:lo + args.batch]
             seeds = np.array([args.seed_base + 100_003 * (c[1] * 1000 + c[2]) + 1_000_000_007 * p + k for c, k in part], dtype=np.uint64)
-            datas = [datafile.make_shoebox(args.box, p, False, seed=int(s)) for s in seeds]
-            eng = E.ShoeboxBatch(datas, seeds=seeds, thresholds=[c[1] for c, _ in part], activations=[c[2] for c, _ in part])
+            if args.ic == "bundled":
+                import dataclasses
+                z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "bundled_ic_bs11.npz"))
+                d0 = datafile.make_shoebox(11, p, False, seed=0)
+                datas = dataclasses.replace(d0, x=z[f"x{p}"].astype(np.float64), types=z[f"t{p}"].astype(np.int32))
+            else:
+                datas = [datafile.make_shoebox(args.box, p, False, seed=int(s)) for s in seeds]
+            eng = E.ShoeboxBatch(datas, n_replicas=len(part), seeds=seeds, thresholds=[c[1] for c, _ in part], activations=[c[2] for c, _ in part])
             eng.set_schedule(args.chunks, observe=True)
             t0 = time.time()
             eng.run()

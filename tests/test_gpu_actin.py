@@ -69,7 +69,7 @@ def _event_plans(indices):
 
 
 def test_actin_events_match_the_restatement(oracle_lib, actin_setup):
-    """a20: nucleation, plus/minus-end polymerisation and minus-end depolymerisation on the device against
+    """a20: nucleation, plus/minus-end polymerisation and minus-/plus-end depolymerisation on the device against
     oracle/actin.py (run_single_shoebox.py:969-1298 with the shared Philox stream), event by event on the same
     coordinates: relocated positions bit for bit, free_actin / filament_details in the reference's list order;
     then the topology the device derived (bonds, angles, 1-2/1-3/1-4 exclusions) through the force parity hook."""
@@ -94,7 +94,8 @@ def test_actin_events_match_the_restatement(oracle_lib, actin_setup):
     md = P.chunk_schedule("shoebox", "LatB", n_chunks=21)[20]
     md = P.ChunkPlan(md.index, md.pair, md.ramp, md.adapt_soft, md.adapt_bond1, md.adapt_bond2, 40)
     n_nucleated = n_grown = n_released = 0
-    for i in (39, 40, 41, 42, 43, 44, 45, 46, 80):
+    assert P.actin_flags(4000) == 15 and P.actin_flags(3999) == 1        # plus-end release: i % t_off_plus == 0 only (:496, 1220)
+    for i in (39, 40, 41, 42, 43, 44, 45, 46, 80, 4000):
         x_pre, _, _ = eng.state()
         eng.set_schedule(plans=_event_plans([i]), observe=True)
         eng.run(0, 1)
@@ -112,6 +113,8 @@ def test_actin_events_match_the_restatement(oracle_lib, actin_setup):
             assert hist[r, 0].sum() <= count
             after = (len(orc[r].filament_details), sum(len(f) for f in orc[r].filament_details))
             n_nucleated += max(after[0] - before[0], 0); n_grown += max(after[1] - before[1], 0); n_released += P.actin_flags(i) & 4 and 1
+            if i == 4000:                                   # both ends released: every surviving filament lost two beads (plus what it grew)
+                assert before[0] > 0 and all(len(f) >= 2 for f in orc[r].filament_details)
         assert st["free"][0] == st["free"][2] and st["free"][0] != st["free"][1]          # same seed, same events
         eng.set_schedule(plans=[md], observe=False)                                    # move on: 40 MD steps, no events
         eng.run(0, 1)
