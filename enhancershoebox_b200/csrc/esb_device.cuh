@@ -34,7 +34,7 @@
 #endif
                                      // overflow it (LAMMPS: neigh_modify one 10000 page 100000, run_single_shoebox.py:533)
 #ifndef ESB_BUILD_REVERSE
-#define ESB_BUILD_REVERSE 1
+#define ESB_BUILD_REVERSE 0              // 1: hand out the build's quads last class first (paid with the full list of round 1; -0.7 % with the half list)
 #endif
 #define ESB_NCLASS 6                 // species classes for the row sort: chromatin-like, actin, RBP, RNP, Ser5P, gene body (induced/active)
 #define ESB_N_COUNTERS 12             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases, dangerous builds, max |pair force| * 256

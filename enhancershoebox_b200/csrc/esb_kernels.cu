@@ -189,7 +189,7 @@ __device__ __forceinline__ float4 lds128(const unsigned int addr)
 // ten times the median).  Level c = the c-th chunk of every quad that has one; the lengths are sorted, so level c is the
 // first Q_c quads and item t is found from the running sums of Q_c.
 #ifndef ESB_ITEM_ROUNDS
-#define ESB_ITEM_ROUNDS 8
+#define ESB_ITEM_ROUNDS 16
 #endif
 #define ESB_CHUNK (ESB_ITEM_ROUNDS * ESB_G)      // entries of one bead per item
 #ifndef ESB_CUT32
@@ -462,17 +462,15 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
                 int ka = 0, kb = 0;
                 if (slot >= 0) { ka = slot ? (int)S.cend[slot - 1] : 0; kb = (int)S.cend[slot]; }
                 if (ESB_HALF) ka = min(max(ka, spos_min + 1), kb);   // nothing at or before the quad's first bead can be listed
-                {   // first bead with x >= xlo, then first bead with x > xhi
-                    int lo_ = ka, hi_ = kb;
-                    while (__any_sync(FULL, lo_ < hi_)) {
+                {   // first bead with x >= xlo and first bead with x > xhi: the two binary searches advance together
+                    // (two shared-memory loads in flight per round, half the loop control)
+                    int lo_ = ka, hi_ = kb, lo2 = ka, hi2 = kb;
+                    while (__any_sync(FULL, (lo_ < hi_) | (lo2 < hi2))) {
                         if (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (S.xs[mid] < xlo) lo_ = mid + 1; else hi_ = mid; }
+                        if (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (S.xs[mid] <= xhi) lo2 = mid + 1; else hi2 = mid; }
                     }
                     ka = lo_;
-                    hi_ = kb;
-                    while (__any_sync(FULL, lo_ < hi_)) {
-                        if (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (S.xs[mid] <= xhi) lo_ = mid + 1; else hi_ = mid; }
-                    }
-                    kb = lo_;
+                    kb = max(lo2, lo_);
                 }
                 const int len = kb - ka;
                 int incl = len;
@@ -663,12 +661,16 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
                 const int kind = term.y & 0xff, type = (term.y >> 8) & 0xff;
                 if (kind == 0) break;                                         // a bead's terms are stored without gaps
                 const float4 pa = S.pos[term.x & 0xffffu];
+                // (reciprocal square roots, MUFU.RSQ, ~2 ulp, instead of sqrt and three divisions per term: a third of the
+                // phase's instructions; the bonded forces stay within 1e-6 of the fp64 oracle's)
                 if (kind == 1) {
                     const float dx = pi.x - pa.x, dy = pi.y - pa.y, dz = pi.z - pa.z;
-                    const float rr = sqrtf(dx * dx + dy * dy + dz * dz);
+                    const float r2b = dx * dx + dy * dy + dz * dz;
+                    const float ri = rsqrtf(r2b);
+                    const float rr = r2b * ri;
                     const float dr = rr - (type == 1 ? r0_1 : r0_2);
                     const float rk = a.bond_k[type] * dr;
-                    const float fb = (rr > 0.0f) ? -2.0f * rk / rr : 0.0f;
+                    const float fb = (r2b > 0.0f) ? -2.0f * rk * ri : 0.0f;
                     fx += dx * fb; fy += dy * fb; fz += dz * fb;
                     if (ENERGY) e_bond += 0.5 * (double)(rk * dr);   // each bond is visited from both ends
                     continue;
@@ -680,20 +682,20 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
                     const float d1x = pi.x - pa.x, d1y = pi.y - pa.y, d1z = pi.z - pa.z;
                     const float d2x = pb.x - pa.x, d2y = pb.y - pa.y, d2z = pb.z - pa.z;
                     const float rsq1 = d1x * d1x + d1y * d1y + d1z * d1z, rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
-                    const float r1r2 = sqrtf(rsq1) * sqrtf(rsq2);
-                    float c = (d1x * d2x + d1y * d2y + d1z * d2z) / r1r2;
+                    const float ri1 = rsqrtf(rsq1), ri2 = rsqrtf(rsq2), ri12 = ri1 * ri2;
+                    float c = (d1x * d2x + d1y * d2y + d1z * d2z) * ri12;
                     c = fminf(fmaxf(c, -1.0f), 1.0f);
-                    const float a11 = k * c / rsq1, a12 = -k / r1r2;
+                    const float a11 = k * c * (ri1 * ri1), a12 = -k * ri12;
                     fx += a11 * d1x + a12 * d2x; fy += a11 * d1y + a12 * d2y; fz += a11 * d1z + a12 * d2z;
                 } else {
                     // this bead is the vertex (i2); pa = i1, pb = i3
                     const float d1x = pa.x - pi.x, d1y = pa.y - pi.y, d1z = pa.z - pi.z;
                     const float d2x = pb.x - pi.x, d2y = pb.y - pi.y, d2z = pb.z - pi.z;
                     const float rsq1 = d1x * d1x + d1y * d1y + d1z * d1z, rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
-                    const float r1r2 = sqrtf(rsq1) * sqrtf(rsq2);
-                    float c = (d1x * d2x + d1y * d2y + d1z * d2z) / r1r2;
+                    const float ri1 = rsqrtf(rsq1), ri2 = rsqrtf(rsq2), ri12 = ri1 * ri2;
+                    float c = (d1x * d2x + d1y * d2y + d1z * d2z) * ri12;
                     c = fminf(fmaxf(c, -1.0f), 1.0f);
-                    const float a11 = k * c / rsq1, a12 = -k / r1r2, a22 = k * c / rsq2;
+                    const float a11 = k * c * (ri1 * ri1), a12 = -k * ri12, a22 = k * c * (ri2 * ri2);
                     fx -= (a11 * d1x + a12 * d2x) + (a22 * d2x + a12 * d1x);
                     fy -= (a11 * d1y + a12 * d2y) + (a22 * d2y + a12 * d1y);
                     fz -= (a11 * d1z + a12 * d2z) + (a22 * d2z + a12 * d1z);
