@@ -320,6 +320,13 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     k.ramp_soft[0] = 0.0; k.ramp_soft[1] = 60.0;          // variable prefactor equal ramp(0,60)         (:627)
     k.nry = h->nry; k.nrz = h->nrz; k.nrows = h->nry * h->nrz;
     k.row_inv = (float)(1.0 / h->cell_edge);
+    {   // as many x buckets per row as the slot table (2 bytes per slot, <= n_pad - 16 slots) leaves room for, at most 6
+        const int cap = h->n_pad - 16;
+        int nxb = getenv("ESB_NXB") ? atoi(getenv("ESB_NXB")) : 6;
+        while (nxb > 1 && (long long)k.nrows * ESB_NCLASS * nxb > cap) nxb--;
+        k.nxb = nxb < 1 ? 1 : nxb;
+        k.xb_inv = (float)(k.nxb / (h->hi[0] - h->lo[0]));
+    }
     k.qcx = h->qcx; k.qcy = h->qcy; k.qcz = h->qcz; k.qcell_inv = (float)(1.0 / h->quad_edge);
     k.pos4 = h->d_pos4; k.vel4 = h->d_vel4; k.bref4 = h->d_bref4; k.rs = h->d_rs; k.frozen = h->d_frozen;
     k.bterm = h->d_bterm; k.spec = h->d_spec; k.n_topo_pad = h->n_topo_pad;

@@ -100,6 +100,8 @@ struct KArgs {
     // row grid of the list build: rows of edge 1/row_inv over (y, z), full length in x
     int nry, nrz, nrows;
     float row_inv;
+    int nxb;                  // x buckets per row (slots of the candidate sort = class x row x bucket)
+    float xb_inv;
     // cubes that group the beads into quads (build order)
     int qcx, qcy, qcz;
     float qcell_inv;

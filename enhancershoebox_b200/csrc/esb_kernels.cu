@@ -139,7 +139,7 @@ __device__ __forceinline__ Smem carve(const KArgs &a, const bool first_buffer = 
     S.gy = S.gx + a.n_topo_pad;
     S.gz = S.gy + a.n_topo_pad;
     S.cend = reinterpret_cast<unsigned short *>(S.fx);
-    S.sidx = S.cend + ((a.nrows * ESB_NCLASS + 2 + 7) & ~7);
+    S.sidx = S.cend + ((a.nrows * ESB_NCLASS * a.nxb + 2 + 7) & ~7);
     S.xs = reinterpret_cast<float *>(S.sidx + 2 * np);
     S.spos = reinterpret_cast<unsigned short *>(S.xs + np);
     return S;
@@ -236,7 +236,9 @@ __device__ __forceinline__ int slot_of(const KArgs &a, const float4 p)
 {
     const int ry = cell_coord(p.y, a.lo[1], a.row_inv, a.nry);
     const int rz = cell_coord(p.z, a.lo[2], a.row_inv, a.nrz);
-    return a.class_of[__float_as_int(p.w) & 0xff] * a.nrows + rz * a.nry + ry;
+    // (a row is cut into nxb buckets along x, x-minor: the row stays one contiguous, x-ordered range of the sorted order,
+    // while the rank sort inside a slot -- quadratic in the slot's population -- sees a sixth of a dense row)
+    return (a.class_of[__float_as_int(p.w) & 0xff] * a.nrows + rz * a.nry + ry) * a.nxb + cell_coord(p.x, a.lo[0], a.xb_inv, a.nxb);
 }
 
 // Counting sort of the beads into `nslots` slots (CTA-wide; called by all threads).  Afterwards S.cend[s] is
@@ -312,7 +314,8 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
     const int tid = threadIdx.x, n = a.n_atoms;
     const int lane = tid & 31, warp = tid >> 5;
     const int nrows = a.nrows, nry = a.nry, nrz = a.nrz;
-    const int nslots = nrows * ESB_NCLASS;
+    const int nxb = a.nxb;
+    const int nslots = nrows * ESB_NCLASS * nxb;
     if (tid == 0) { S.misc[M_CURLIST] = 0; S.misc[M_QCTR] = 0; }
     // ---- (A) quad order: beads grouped by (class, cube of edge ~2.2), by atom index inside a group.  Four
     //      consecutive beads of this order form a quad: same species, close together, hence a small bounding box.
@@ -414,8 +417,8 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
             if (lane < ESB_NCLASS) {
                 const float *rc = S.setup->reach + lane;
                 const float c = fmaxf(fmaxf(rc[ta[0] * 8], rc[ta[1] * 8]), fmaxf(rc[ta[2] * 8], rc[ta[3] * 8]));
-                const int first = lane * nrows;
-                const int pop = (int)S.cend[first + nrows - 1] - (first ? (int)S.cend[first - 1] : 0);
+                const int first = lane * nrows * nxb;
+                const int pop = (int)S.cend[first + nrows * nxb - 1] - (first ? (int)S.cend[first - 1] : 0);
                 if (c > 0.0f && pop > 0 && (!ESB_HALF || lane >= cls_min)) {
                     const int y0 = cell_coord(ymin - c, loy, rinv, nry), y1 = cell_coord(ymax + c, loy, rinv, nry);
                     int z0 = cell_coord(zmin - c, loz, rinv, nrz);
@@ -460,7 +463,7 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
                 }
                 const float xlo = xmin - reach, xhi = xmax + reach;
                 int ka = 0, kb = 0;
-                if (slot >= 0) { ka = slot ? (int)S.cend[slot - 1] : 0; kb = (int)S.cend[slot]; }
+                if (slot >= 0) { ka = slot ? (int)S.cend[slot * nxb - 1] : 0; kb = (int)S.cend[slot * nxb + nxb - 1]; }     // the row: all its x buckets
                 if (ESB_HALF) ka = min(max(ka, spos_min + 1), kb);   // nothing at or before the quad's first bead can be listed
                 {   // first bead with x >= xlo and first bead with x > xhi: the two binary searches advance together
                     // (two shared-memory loads in flight per round, half the loop control)
