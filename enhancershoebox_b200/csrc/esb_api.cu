@@ -90,7 +90,7 @@ struct esb_handle {
     double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     bool have_box = false, have_topo = false, have_soft = false, have_tables = false, have_layout = false, have_state = false;
     bool setups_dirty = true;
-    double dt = 0.005, t_target = 1.0, t_damp = 0.5, wall_eps = 100.0, wall_cut = 3.0, skin = 0.3, cell_edge = 2.8, quad_edge = 2.2;
+    double dt = 0.005, t_target = 1.0, t_damp = 0.5, wall_eps = 100.0, wall_cut = 3.0, skin = 0.3, cell_edge = 2.8, xcell_edge = 1.0;
     int neigh_delay = 10;
     int langevin_mode = 1;
     double bond_k[3] = {0, 90.0, 90.0}, bond_r0[3] = {0, 1.0, 0.3}, angle_k[3] = {0, 100.0 / 60.0, 33.0};
@@ -143,7 +143,7 @@ struct esb_handle {
     size_t smem_per_sm = 233472;
     Layout lay = {0, 0, 0, 0};
     std::vector<ReplicaScalars> rs_host;
-    int nry = 1, nrz = 1, qcx = 1, qcy = 1, qcz = 1;
+    int nry = 1, nrz = 1, ncx = 1;
 };
 
 namespace {
@@ -190,11 +190,11 @@ const unsigned char k_class_of[ESB_MAXT] = {0, 0, 0, 1, 2, 3, 5, 5, 4, 0, 0, 0};
 int rebuild_setups(esb_handle *h)
 {
     if (!h->have_box) return fail(ESB_ESTATE, "esb_set_box must be called first");
-    // ---- row grid of the list build: rows over (y, z) of edge row_edge, every row spans the box in x.
-    //      The build scratch (the 3 force arrays, 12 n_pad bytes) holds the (class, row) table (2 B per slot),
-    //      three u16 index arrays and the sorted x coordinates (4 B per bead): slots + 2 <= n_pad.  The build packs
-    //      a quad's first row and row count in y and z into 8 bits each.
-    const int cap = h->n_pad - 16;
+    // ---- cell grid of the list build: rows over (y, z) of edge cell_edge, every row cut into cells of edge xcell_edge
+    //      along x.  The build scratch (the 3 force arrays, 12 n_pad bytes) holds the (class, row, x cell) table (2 B per
+    //      slot), one u16 index array and the list lengths (4 B per bead): slots + 2 <= 3 n_pad - 16.  The build packs
+    //      a bead's first row and row count in y and z into 8 bits each.
+    const int cap = 3 * h->n_pad - 32;
     double c = h->cell_edge;
     for (;;) {
         h->nry = std::max(1, (int)ceil((h->hi[1] - h->lo[1]) / c));
@@ -203,17 +203,8 @@ int rebuild_setups(esb_handle *h)
         c *= 1.05;
     }
     h->cell_edge = c;
-    // cubes of the quad order: table (2 B per (class, cube)) + one u16 index array in the same scratch
-    const int capq = 5 * h->n_pad - 16;
-    double qc = h->quad_edge;
-    for (;;) {
-        h->qcx = std::max(1, (int)ceil((h->hi[0] - h->lo[0]) / qc));
-        h->qcy = std::max(1, (int)ceil((h->hi[1] - h->lo[1]) / qc));
-        h->qcz = std::max(1, (int)ceil((h->hi[2] - h->lo[2]) / qc));
-        if ((long long)h->qcx * h->qcy * h->qcz * ESB_NCLASS <= capq) break;
-        qc *= 1.05;
-    }
-    h->quad_edge = qc;
+    h->ncx = std::max(1, (int)ceil((h->hi[0] - h->lo[0]) / h->xcell_edge));
+    h->ncx = std::max(1, std::min(h->ncx, cap / (h->nry * h->nrz * ESB_NCLASS)));
 
     const int nt = (int)h->tables.size();
     std::vector<DevTab> closed(nt), arr(nt);
@@ -319,15 +310,8 @@ int fill_kargs(esb_handle *h, KArgs &k, bool array_flavour)
     k.ramp_bond[2][0] = 0.033; k.ramp_bond[2][1] = 0.3;   // variable actinr0 equal ramp(0.033,0.3)      (:638)
     k.ramp_soft[0] = 0.0; k.ramp_soft[1] = 60.0;          // variable prefactor equal ramp(0,60)         (:627)
     k.nry = h->nry; k.nrz = h->nrz; k.nrows = h->nry * h->nrz;
-    k.row_inv = (float)(1.0 / h->cell_edge);
-    {   // as many x buckets per row as the slot table (2 bytes per slot, <= n_pad - 16 slots) leaves room for, at most 6
-        const int cap = h->n_pad - 16;
-        int nxb = getenv("ESB_NXB") ? atoi(getenv("ESB_NXB")) : 6;
-        while (nxb > 1 && (long long)k.nrows * ESB_NCLASS * nxb > cap) nxb--;
-        k.nxb = nxb < 1 ? 1 : nxb;
-        k.xb_inv = (float)(k.nxb / (h->hi[0] - h->lo[0]));
-    }
-    k.qcx = h->qcx; k.qcy = h->qcy; k.qcz = h->qcz; k.qcell_inv = (float)(1.0 / h->quad_edge);
+    k.row_inv = (float)(1.0 / h->cell_edge); k.row_edge = (float)h->cell_edge;
+    k.ncx = h->ncx; k.xc_inv = (float)(h->ncx / (h->hi[0] - h->lo[0]));
     k.pos4 = h->d_pos4; k.vel4 = h->d_vel4; k.bref4 = h->d_bref4; k.rs = h->d_rs; k.frozen = h->d_frozen;
     k.bterm = h->d_bterm; k.spec = h->d_spec; k.n_topo_pad = h->n_topo_pad;
     k.bterm_stride = h->bterm_stride; k.spec_stride = h->spec_stride;
@@ -387,7 +371,7 @@ int esb_create(int device, int n_replicas, int n_atoms, int n_types, esb_handle 
     if (const char *s = getenv("ESB_SKIN")) h->skin = atof(s);
     if (const char *s = getenv("ESB_DELAY")) h->neigh_delay = atoi(s);
     if (const char *s = getenv("ESB_CELL")) h->cell_edge = atof(s);
-    if (const char *s = getenv("ESB_QCELL")) h->quad_edge = atof(s);
+    if (const char *s = getenv("ESB_XCELL")) h->xcell_edge = atof(s);
     memset(h->soft_cut, 0, sizeof(h->soft_cut));
     memset(h->maps, 0, sizeof(h->maps));
     h->frozen.assign(h->n_pad, 0);

@@ -97,14 +97,12 @@ struct KArgs {
     float bond_k[3], angle_k[3];
     double ramp_bond[3][2];   // ramp(v0,v1) of fix s2/s3 per bond type
     double ramp_soft[2];
-    // row grid of the list build: rows of edge 1/row_inv over (y, z), full length in x
+    // cell grid of the list build: rows of edge row_edge = 1/row_inv over (y, z), every row cut into ncx cells of edge
+    // 1/xc_inv along x; slots of the candidate sort = (class, z row, y row, x cell), x-minor
     int nry, nrz, nrows;
-    float row_inv;
-    int nxb;                  // x buckets per row (slots of the candidate sort = class x row x bucket)
-    float xb_inv;
-    // cubes that group the beads into quads (build order)
-    int qcx, qcy, qcz;
-    float qcell_inv;
+    float row_inv, row_edge;
+    int ncx;
+    float xc_inv;
     // device arrays
     float4 *pos4;             // [R][n_pad] x,y,z,type bits
     float4 *vel4;             // [R][n_pad]

@@ -54,11 +54,9 @@ struct Smem {
     int *misc;                   // see M_* below
     double *dmisc;
     // aliases into the force region, valid only inside build_lists()
-    unsigned short *cend;        // [nslots + 2]  running end offset of every slot
-    unsigned short *sidx;        // [n_pad]       atom indices sorted by (slot, x); a second [n_pad] block behind it is sort scratch
-    float *xs;                   // [n_pad]       x of the sorted beads
-    unsigned short *spos;        // [n_pad]       position of every bead in the sorted (candidate) order
-    unsigned short *qord;        // [n_pad]       quad order of the build (own region: it outlives the scratch reuse)
+    unsigned short *cend;        // [-1 .. nslots + 2]  running end offset of every slot (cend[-1] = 0)
+    unsigned short *sidx;        // [n_pad]       atom indices in candidate order: sorted by (slot, atom index)
+    int *cnt;                    // [n_pad]       list length of every bead (first the scratch of the sort)
     unsigned char *owner;        // [n_pad]       cluster variant: rank of the CTA that owns the bead (its force quad)
     float4 *pos_next;            // cluster variant: the other position buffer (written by the per-atom phase of all CTAs)
     unsigned short *mine;        // cluster variant: the beads this CTA owns (any order), misc[M_NMINE] of them
@@ -88,7 +86,6 @@ __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables, int n_
     b += ((size_t)n_tables * sizeof(DevTab) + 15) & ~(size_t)15;
     b += ((size_t)M_END * 4 + 15) & ~(size_t)15;
     b += (size_t)D_END * 8;
-    b += (size_t)n_pad * 2;                  // quad order
 #if ESB_CLUSTER
     b += ((size_t)n_pad + 15) & ~(size_t)15; // bead owners
     b += (size_t)n_pad * 16;                 // second position buffer (the CTAs of a cluster write the next positions there)
@@ -120,7 +117,6 @@ __device__ __forceinline__ Smem carve(const KArgs &a, const bool first_buffer = 
     S.tab = reinterpret_cast<DevTab *>(base + o); o += ((size_t)a.n_tables * sizeof(DevTab) + 15) & ~(size_t)15;
     S.dmisc = reinterpret_cast<double *>(base + o); o += (size_t)D_END * 8;
     S.misc = reinterpret_cast<int *>(base + o); o += ((size_t)M_END * 4 + 15) & ~(size_t)15;
-    S.qord = reinterpret_cast<unsigned short *>(base + o); o += (size_t)np * 2;
     S.owner = reinterpret_cast<unsigned char *>(base + o);
 #if ESB_CLUSTER
     o += ((size_t)np + 15) & ~(size_t)15;
@@ -138,10 +134,9 @@ __device__ __forceinline__ Smem carve(const KArgs &a, const bool first_buffer = 
     S.gx = reinterpret_cast<float *>(base + o);
     S.gy = S.gx + a.n_topo_pad;
     S.gz = S.gy + a.n_topo_pad;
-    S.cend = reinterpret_cast<unsigned short *>(S.fx);
-    S.sidx = S.cend + ((a.nrows * ESB_NCLASS * a.nxb + 2 + 7) & ~7);
-    S.xs = reinterpret_cast<float *>(S.sidx + 2 * np);
-    S.spos = reinterpret_cast<unsigned short *>(S.xs + np);
+    S.cend = reinterpret_cast<unsigned short *>(S.fx) + 2;
+    S.sidx = S.cend + 6 + ((a.nrows * ESB_NCLASS * a.ncx + 2 + 7) & ~7);
+    S.cnt = reinterpret_cast<int *>(S.sidx + np);
     return S;
 }
 
@@ -195,6 +190,9 @@ __device__ __forceinline__ float4 lds128(const unsigned int addr)
 #ifndef ESB_CUT32
 #define ESB_CUT32 1
 #endif
+#ifndef ESB_ITEM_ORDER
+#define ESB_ITEM_ORDER 1
+#endif
 #ifndef ESB_FGUARD
 #define ESB_FGUARD 1
 #endif
@@ -231,19 +229,19 @@ __device__ __forceinline__ int cell_coord(float x, float lo, float inv, int n)
     return min(max(c, 0), n - 1);
 }
 
-// slot of a bead in the row sort: (species class, z row, y row), class-major
+// slot of a bead in the candidate sort: (species class, z row, y row, x cell), class-major and x-minor: a row is one
+// contiguous range of the sorted order, and so is every run of consecutive x cells of a row
 __device__ __forceinline__ int slot_of(const KArgs &a, const float4 p)
 {
     const int ry = cell_coord(p.y, a.lo[1], a.row_inv, a.nry);
     const int rz = cell_coord(p.z, a.lo[2], a.row_inv, a.nrz);
-    // (a row is cut into nxb buckets along x, x-minor: the row stays one contiguous, x-ordered range of the sorted order,
-    // while the rank sort inside a slot -- quadratic in the slot's population -- sees a sixth of a dense row)
-    return (a.class_of[__float_as_int(p.w) & 0xff] * a.nrows + rz * a.nry + ry) * a.nxb + cell_coord(p.x, a.lo[0], a.xb_inv, a.nxb);
+    return (a.class_of[__float_as_int(p.w) & 0xff] * a.nrows + rz * a.nry + ry) * a.ncx + cell_coord(p.x, a.lo[0], a.xc_inv, a.ncx);
 }
 
 // Counting sort of the beads into `nslots` slots (CTA-wide; called by all threads).  Afterwards S.cend[s] is
-// the END offset of slot s (start = S.cend[s-1], 0 for s = 0) and `tmp` holds the bead indices grouped by slot,
-// in arbitrary order inside a slot.  The counters are u16 packed in pairs for the shared-memory atomics.
+// the END offset of slot s (start = S.cend[s-1]; S.cend[-1] is a zero that belongs to the array) and `tmp` holds the
+// bead indices grouped by slot, in arbitrary order inside a slot.  The counters are u16 packed in pairs for the
+// shared-memory atomics.
 template <class SlotFn>
 __device__ __forceinline__ void slot_sort(const Smem &S, const KArgs &a, const int nslots, unsigned short *tmp, SlotFn slot_fn)
 {
@@ -252,6 +250,7 @@ __device__ __forceinline__ void slot_sort(const Smem &S, const KArgs &a, const i
     unsigned int *cw = reinterpret_cast<unsigned int *>(S.cend);
     const int ncw = (nslots + 2 + 1) >> 1;
     for (int w = tid; w < ncw; w += ESB_THREADS) cw[w] = 0u;
+    if (tid == 0) cw[-1] = 0u;                                       // S.cend[-1] (and the unused half word before it)
     __syncthreads();
     // count (slot s is stored at position s+1 so that, after the scan, position s holds start(s))
     for (int i = tid; i < n; i += ESB_THREADS) {
@@ -291,139 +290,100 @@ __device__ __forceinline__ void slot_sort(const Smem &S, const KArgs &a, const i
 // ------------------------------------------------------------------------------------------------
 // Neighbour list build.  Stands in for LAMMPS' binned neighbour build (`neighbor 0.3 multi`,
 // `neigh_modify every 1 delay 10 check yes`, run_single_shoebox.py:532-533): per-type-pair
-// cutoff + skin, 1-2/1-3/1-4 partners excluded (default special_bonds).  Full list (both i->j and
-// j->i) so the force loop needs no scatter; every entry carries the pair's table id.
+// cutoff + skin, 1-2/1-3/1-4 partners excluded (default special_bonds); every entry carries the pair's table id.
 //
-// Beads are counting-sorted into slots = (species class, row), a row being a (y, z) column of edge
-// 2.8 that spans the box in x, and ordered by x inside a slot.  The candidates of a bead towards
-// class B are then, for every row within reach(type, B) in y and z, ONE contiguous span of the sorted
-// order: the beads of that row with x within reach -- found by binary search, at full resolution in x
-// and with the cutoff of that class pair (0.7 for RBP-RBP ... 3.2 for RNP-RNP) instead of the
-// largest cutoff of the bead.  The build walks the sorted order four beads ("quad": same class,
-// same or adjacent row, adjacent in x) per warp: the lanes first resolve the quad's spans (one span
-// per lane), then run through the concatenation of the spans 32 candidates at a time; every lane
-// tests its candidate against all four beads (128 distance tests per iteration) and accepted
-// (bead, j) pairs are ballot-compacted into the bead's arena.  Lists are deterministic (the sorted
-// order is a function of the positions only).  Afterwards the descriptors are re-sorted by list
-// length: that is the order in which the force loop forms its quads.
+// Beads are counting-sorted into slots = (species class, z row, y row, x cell) -- rows of edge 2.8 over (y, z), cut
+// into cells of edge ~1 along x -- by atom index inside a slot ("candidate order").  The candidates of ONE bead towards
+// class B are then, for every row within reach(type, B) in y and z, one contiguous span of that order: the cells of the
+// row within sqrt(reach^2 - d^2) in x, d being the distance from the bead to the row's slab -- two table look-ups per
+// span, no search, and the cutoff of that class pair (0.6 for RBP-RBP ... 3.0 for RNP-RNP) instead of the bead's
+// largest.  A warp takes four consecutive beads of the candidate order at a time: lanes 0..23 work out the row ranges of
+// the 4 x 6 (bead, class) combinations, then the lanes resolve the spans of all four beads (one span per lane and round),
+// prefix-sum their lengths and run through the concatenation 32 candidates at a time, ONE (bead, candidate) pair per
+// lane.  An accepted pair takes its place in the bead's arena from a shared-memory counter (atomic: the order of a list
+// is immaterial, the force sums are integers).  Half list: bead i keeps candidate j only when j comes after i in
+// candidate order, so classes before the bead's own and rows before its own are never scanned and every span is
+// clipped to the positions behind the bead.  (Round 2 scanned the bounding box of a quad of beads over whole rows with
+// binary searches in x: 8 times the distance tests.)  Afterwards the descriptors are sorted by list length: that is
+// the order in which the force loop forms its quads.
 // ------------------------------------------------------------------------------------------------
+#if defined(ESB_BUILD_PROF) && ESB_BUILD_PROF      // experiments: the build's sort goes to the per-atom timer, thread 0's batches to the observe timer
+#define ESB_BP_TICK(acc) { if (tid == 0) { long long *L_ = reinterpret_cast<long long *>(S.dmisc); const long long now_ = clock64(); L_[acc] += now_ - L_[L_TMARK]; L_[L_TMARK] = now_; } }
+#else
+#define ESB_BP_TICK(acc)
+#endif
 template <int NP, bool P16>
 __device__ __noinline__ void build_lists(const KArgs &a, const int r)
 {
     const Smem S = carve<NP>(a);
     const int tid = threadIdx.x, n = a.n_atoms;
     const int lane = tid & 31, warp = tid >> 5;
-    const int nrows = a.nrows, nry = a.nry, nrz = a.nrz;
-    const int nxb = a.nxb;
-    const int nslots = nrows * ESB_NCLASS * nxb;
+    const int nrows = a.nrows, nry = a.nry, nrz = a.nrz, ncx = a.ncx;
+    const int nslots = nrows * ESB_NCLASS * ncx;
     if (tid == 0) { S.misc[M_CURLIST] = 0; S.misc[M_QCTR] = 0; }
-    // ---- (A) quad order: beads grouped by (class, cube of edge ~2.2), by atom index inside a group.  Four
-    //      consecutive beads of this order form a quad: same species, close together, hence a small bounding box.
+    // ---- candidate order: beads grouped by (class, row, x cell), by atom index inside a cell ----
     {
-        const int nq_slots = a.qcx * a.qcy * a.qcz * ESB_NCLASS;
-        unsigned short *tmp = S.cend + ((nq_slots + 2 + 7) & ~7);
-        auto cube_of = [&](const float4 p) {
-            const int cx = cell_coord(p.x, a.lo[0], a.qcell_inv, a.qcx);
-            const int cy = cell_coord(p.y, a.lo[1], a.qcell_inv, a.qcy);
-            const int cz = cell_coord(p.z, a.lo[2], a.qcell_inv, a.qcz);
-            return ((a.class_of[__float_as_int(p.w) & 0xff] * a.qcz + cz) * a.qcy + cy) * a.qcx + cx;
-        };
-        slot_sort(S, a, nq_slots, tmp, cube_of);
-        for (int i = tid; i < n; i += ESB_THREADS) {
-            const int slot = cube_of(S.pos[i]);
-            const int s0 = slot ? S.cend[slot - 1] : 0, s1 = S.cend[slot];
-            int rank = 0;
-            for (int q = s0; q < s1; q++) rank += (tmp[q] < (unsigned short)i);
-            S.qord[s0 + rank] = (unsigned short)i;
-        }
-        __syncthreads();
-    }
-    // ---- (B) candidate order: beads grouped by (class, row), by (x, atom index) inside a row ----
-    {
-        unsigned short *tmp = S.sidx + a.n_pad;
-        auto row_of = [&](const float4 p) { return slot_of(a, p); };
-        slot_sort(S, a, nslots, tmp, row_of);
+        unsigned short *tmp = reinterpret_cast<unsigned short *>(S.cnt);
+        auto cell_of = [&](const float4 p) { return slot_of(a, p); };
+        slot_sort(S, a, nslots, tmp, cell_of);
         for (int i = tid; i < n; i += ESB_THREADS) {
             const float4 p = S.pos[i];
             S.bx[i] = p.x; S.by[i] = p.y; S.bz[i] = p.z;
             const int slot = slot_of(a, p);
-            const int s0 = slot ? S.cend[slot - 1] : 0, s1 = S.cend[slot];
+            const int s0 = S.cend[slot - 1], s1 = S.cend[slot];
             int rank = 0;
-            for (int q = s0; q < s1; q++) {
-                const int o = tmp[q];
-                const float xo = S.pos[o].x;
-                rank += (xo < p.x) || (xo == p.x && o < i);
-            }
+            for (int q = s0; q < s1; q++) rank += (tmp[q] < (unsigned short)i);
             S.sidx[s0 + rank] = (unsigned short)i;
-            S.xs[s0 + rank] = p.x;
-            S.spos[i] = (unsigned short)(s0 + rank);
         }
         __syncthreads();
+        for (int i = tid; i < n; i += ESB_THREADS) S.cnt[i] = 0;     // (the sort scratch becomes the list lengths)
+        __syncthreads();
     }
+    ESB_BP_TICK(L_TATOM)
 
     const unsigned int FULL = 0xffffffffu;
-    const unsigned int lt_mask = (1u << lane) - 1u;
-    // P16 (at most 32 tables): 16-bit entries (neighbour | table id << 11), two per word, in list order (the integer
-    // force sums do not depend on the order in which a group's lanes visit the entries); half the list traffic
+    // P16 (at most 32 tables): 16-bit entries (neighbour | table id << 11), two per word; half the list traffic
     constexpr unsigned int ESTRIDE = P16 ? ESB_NL_STRIDE / 2 : ESB_NL_STRIDE;      // arena of a bead in words
     unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESTRIDE;
     unsigned short *pool16 = reinterpret_cast<unsigned short *>(pool);
-    uint2 *qbuild = a.nl_qinfo + ((size_t)r * 2 + 1) * a.n_pad;     // descriptors in build (sorted) order
-    const float loy = a.lo[1], loz = a.lo[2], rinv = a.row_inv;
+    uint2 *qbuild = a.nl_qinfo + ((size_t)r * 2 + 1) * a.n_pad;     // descriptors in build (candidate) order
+    const float lox = a.lo[0], loy = a.lo[1], loz = a.lo[2], rinv = a.row_inv, redge = a.row_edge, xinv = a.xc_inv;
     const int n_topo = a.n_topo;
+    const float *cs_row = S.setup->cutsq_skin;
+    const unsigned char *tab_row = S.setup->tabid;
     unsigned int listed = 0;
-    const int nquads = (n + 3) >> 2;
+    constexpr int NB = 4;                                            // beads per batch: NB * ESB_NCLASS (bead, class) combinations <= 32 lanes
+    static_assert(NB * ESB_NCLASS <= 32, "one lane per (bead, class) combination");
+    const int nbatch = (n + NB - 1) / NB;
+    // this lane's (bead, class) combination of a batch
+    const int cb_bead = lane / ESB_NCLASS, cb_class = lane - cb_bead * ESB_NCLASS;
+    int cb_pop = 0;                                                  // beads of class cb_class
+    if (lane < NB * ESB_NCLASS) cb_pop = (int)S.cend[(cb_class + 1) * nrows * ncx - 1] - (int)S.cend[cb_class * nrows * ncx - 1];
     for (;;) {
-        // quads are handed out dynamically: their cost varies by two orders of magnitude with the species
+        // batches are handed out dynamically: their cost varies by two orders of magnitude with the species
         int q = 0;
         if (lane == 0) q = atomicAdd(&S.misc[M_QCTR], 1);
-        q = __shfl_sync(FULL, q, 0) * csize() + crank();         // (cluster variant: the quads are dealt to the CTAs of the cluster)
-        if (q >= nquads) break;
-        if (ESB_BUILD_REVERSE) q = nquads - 1 - q;               // last classes of the quad order first (gene body, Ser5P, RNP: the long scans)
-        int ia[4], ta[4], cnt[4];
-        int sp_[4];                                              // HALF: position of the bead in the candidate order
-        float4 pa[4];
-        float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f, zmin = 3.0e38f, zmax = -3.0e38f;
-        bool any_topo = false;
-        int cls_min = ESB_NCLASS, spos_min = 0x7fffffff;
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int idx = min(4 * q + b, n - 1);               // the last quad may repeat its last bead
-            ia[b] = S.qord[idx];
-            pa[b] = S.pos[ia[b]];
-            ta[b] = __float_as_int(pa[b].w) & 0xff;
-            cnt[b] = 0;
-            xmin = fminf(xmin, pa[b].x); xmax = fmaxf(xmax, pa[b].x);
-            ymin = fminf(ymin, pa[b].y); ymax = fmaxf(ymax, pa[b].y);
-            zmin = fminf(zmin, pa[b].z); zmax = fmaxf(zmax, pa[b].z);
-            any_topo |= ia[b] < n_topo;
-            if (ESB_HALF) {
-                sp_[b] = S.spos[ia[b]];
-                spos_min = min(spos_min, sp_[b]);
-                cls_min = min(cls_min, (int)a.class_of[ta[b]]);
-            } else sp_[b] = 0;
-        }
-        // HALF list: bead i lists candidate j only when j comes AFTER i in the candidate order (class, row, x), so every
-        // unordered pair is stored -- and evaluated -- once.  Classes before the quad's lowest class hold no such
-        // candidate, and in that class the rows before the quad's first z row hold none either.
-        const int zrow_min = ESB_HALF ? cell_coord(zmin, a.lo[2], a.row_inv, a.nrz) : 0;
-        // spans of the quad: for class B every row within reach of the quad's bounding box; the span list is the
-        // concatenation over the classes.  Lane B < ESB_NCLASS works out and keeps the numbers of class B:
-        // my_pack = first y row | rows in y << 8 | first z row << 16, spans [my_cum, my_end), reach.
-        int my_pack = 0, my_end = 0, my_cum = 0;
+        q = __shfl_sync(FULL, q, 0) * csize() + crank();         // (cluster variant: the batches are dealt to the CTAs of the cluster)
+        if (q >= nbatch) break;
+        if (ESB_BUILD_REVERSE) q = nbatch - 1 - q;               // last classes of the candidate order first (gene body, Ser5P, RNP: the long scans)
+        // ---- the row ranges of the (bead, class) combinations; my_* are valid in lanes 0 .. NB * ESB_NCLASS - 1 ----
+        int my_pack = 0, my_end = 0, my_cum = 0, my_bead = 0;     // first y row | rows in y << 8 | first z row << 16;  atom | candidate position << 11 | type << 22 | class << 26
         float my_reach = 0.0f;
         {
             int nsp = 0;
-            if (lane < ESB_NCLASS) {
-                const float *rc = S.setup->reach + lane;
-                const float c = fmaxf(fmaxf(rc[ta[0] * 8], rc[ta[1] * 8]), fmaxf(rc[ta[2] * 8], rc[ta[3] * 8]));
-                const int first = lane * nrows * nxb;
-                const int pop = (int)S.cend[first + nrows * nxb - 1] - (first ? (int)S.cend[first - 1] : 0);
-                if (c > 0.0f && pop > 0 && (!ESB_HALF || lane >= cls_min)) {
-                    const int y0 = cell_coord(ymin - c, loy, rinv, nry), y1 = cell_coord(ymax + c, loy, rinv, nry);
-                    int z0 = cell_coord(zmin - c, loz, rinv, nrz);
-                    const int z1 = cell_coord(zmax + c, loz, rinv, nrz);
-                    if (ESB_HALF && lane == cls_min) z0 = max(z0, zrow_min);
+            const int sp_i = NB * q + cb_bead;                   // position of the bead in the candidate order
+            if (lane < NB * ESB_NCLASS && sp_i < n) {
+                const int i = S.sidx[sp_i];
+                const float4 pi = S.pos[i];
+                const int ti = __float_as_int(pi.w) & 0xff, cls = a.class_of[ti];
+                const float c = S.setup->reach[ti * 8 + cb_class];
+                my_bead = i | (sp_i << 11) | (ti << 22) | (cls << 26);
+                if (c > 0.0f && cb_pop > 0 && (!ESB_HALF || cb_class >= cls)) {
+                    const int y0 = cell_coord(pi.y - c, loy, rinv, nry), y1 = cell_coord(pi.y + c, loy, rinv, nry);
+                    int z0 = cell_coord(pi.z - c, loz, rinv, nrz);
+                    const int z1 = cell_coord(pi.z + c, loz, rinv, nrz);
+                    // HALF list: in the bead's own class nothing before its own z row comes after it in candidate order
+                    if (ESB_HALF && cb_class == cls) z0 = max(z0, cell_coord(pi.z, loz, rinv, nrz));
                     my_pack = y0 | ((y1 - y0 + 1) << 8) | (z0 << 16);
                     my_reach = c;
                     nsp = (y1 - y0 + 1) * (z1 - z0 + 1);
@@ -431,116 +391,98 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
             }
             my_end = nsp;
 #pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
+            for (int d = 1; d < 32; d <<= 1) {
                 const int t = __shfl_up_sync(FULL, my_end, d);
                 if (lane >= d) my_end += t;
             }
             my_cum = my_end - nsp;
         }
-        const int n_spans = __shfl_sync(FULL, my_end, ESB_NCLASS - 1);
-        // Two warp-uniform specialisations keep the common inner loop short: `uniform` = the four beads
-        // have the same type (one cutoff / table-id row per candidate), `any_topo` = some bead of the quad
-        // is bonded (only then can a candidate be an excluded 1-2/1-3/1-4 partner).
-        const bool uniform = (ta[0] == ta[1]) && (ta[1] == ta[2]) && (ta[2] == ta[3]);
-        const float *cs_row = S.setup->cutsq_skin;
-        const unsigned char *tab_row = S.setup->tabid;
-        auto scan_spans = [&](auto topo_tag, auto uniform_tag) {
-            constexpr bool TOPO = decltype(topo_tag)::value, UNIFORM = decltype(uniform_tag)::value;
-            for (int sp0 = 0; sp0 < n_spans; sp0 += 32) {
-                // ---- this lane's span: (class, row) -> slot -> the beads with x within reach ----
-                const int sp = sp0 + lane;
-                int B = 0;
+        const int n_spans = __shfl_sync(FULL, my_end, 31);
+        for (int sp0 = 0; sp0 < n_spans; sp0 += 32) {
+            // ---- this lane's span: (bead, class, row) -> the cells of the row within reach in x ----
+            const int sp = sp0 + lane;
+            int c = 0;                                           // combination of span sp: the first lane with my_end > sp
 #pragma unroll
-                for (int c = 0; c < ESB_NCLASS; c++) B += (sp >= __shfl_sync(FULL, my_end, c));
-                const int pack = __shfl_sync(FULL, my_pack, B & 7), cumB = __shfl_sync(FULL, my_cum, B & 7);
-                const float reach = __shfl_sync(FULL, my_reach, B & 7);
-                int slot = -1;
-                if (B < ESB_NCLASS) {
-                    const int li = sp - cumB, ny = (pack >> 8) & 0xff;
-                    const int dz = (int)(((float)li + 0.5f) * rcp_approx((float)ny));
-                    const int dy = li - dz * ny;
-                    slot = B * nrows + ((pack >> 16) + dz) * nry + (pack & 0xff) + dy;
+            for (int st = 16; st >= 1; st >>= 1) {
+                const int t = __shfl_sync(FULL, my_end, c + st - 1);
+                if (t <= sp) c += st;
+            }
+            const int pack = __shfl_sync(FULL, my_pack, c & 31), cum = __shfl_sync(FULL, my_cum, c & 31);
+            const int bead = __shfl_sync(FULL, my_bead, c & 31);
+            const float reach = __shfl_sync(FULL, my_reach, c & 31);
+            int ka = 0, kb = 0;
+            if (sp < n_spans) {
+                const int B = c - (c / ESB_NCLASS) * ESB_NCLASS;
+                const int li = sp - cum, ny = (pack >> 8) & 0xff;
+                const int dzr = (int)(((float)li + 0.5f) * rcp_approx((float)ny));
+                const int cy = (pack & 0xff) + li - dzr * ny, cz = (pack >> 16) + dzr;
+                const float4 pi = S.pos[bead & 0x7ff];
+                // distance from the bead to the slab of the row (a little short: the row of a bead comes from a rounded product)
+                const float ylo = fmaf((float)cy, redge, loy), zlo = fmaf((float)cz, redge, loz);
+                const float dy = fmaxf(fmaxf(ylo - pi.y, pi.y - (ylo + redge)) - 1.0e-5f, 0.0f);
+                const float dz = fmaxf(fmaxf(zlo - pi.z, pi.z - (zlo + redge)) - 1.0e-5f, 0.0f);
+                const float rr = fmaf(reach, reach, -fmaf(dy, dy, dz * dz));
+                if (rr > 0.0f) {
+                    const float rx = sqrtf(rr) * 1.000001f;
+                    const int x0 = cell_coord(pi.x - rx, lox, xinv, ncx), x1 = cell_coord(pi.x + rx, lox, xinv, ncx);
+                    const int base = (B * nrows + cz * nry + cy) * ncx;
+                    ka = S.cend[base + x0 - 1];
+                    kb = S.cend[base + x1];
+                    // nothing at or before the bead itself can be listed (its own class only: later classes lie behind it anyway)
+                    if (ESB_HALF) ka = min(max(ka, ((bead >> 11) & 0x7ff) + 1), kb);
                 }
-                const float xlo = xmin - reach, xhi = xmax + reach;
-                int ka = 0, kb = 0;
-                if (slot >= 0) { ka = slot ? (int)S.cend[slot * nxb - 1] : 0; kb = (int)S.cend[slot * nxb + nxb - 1]; }     // the row: all its x buckets
-                if (ESB_HALF) ka = min(max(ka, spos_min + 1), kb);   // nothing at or before the quad's first bead can be listed
-                {   // first bead with x >= xlo and first bead with x > xhi: the two binary searches advance together
-                    // (two shared-memory loads in flight per round, half the loop control)
-                    int lo_ = ka, hi_ = kb, lo2 = ka, hi2 = kb;
-                    while (__any_sync(FULL, (lo_ < hi_) | (lo2 < hi2))) {
-                        if (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (S.xs[mid] < xlo) lo_ = mid + 1; else hi_ = mid; }
-                        if (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (S.xs[mid] <= xhi) lo2 = mid + 1; else hi2 = mid; }
-                    }
-                    ka = lo_;
-                    kb = max(lo2, lo_);
+            }
+            const int len = kb - ka;
+            int incl = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            const int shift = ka - (incl - len);                 // candidate f of this span sits at sorted position f + shift
+            // ---- the concatenated spans, 32 (bead, candidate) pairs per iteration ----
+            for (int f0 = 0; f0 < total; f0 += 32) {
+                const int f = f0 + lane;
+                const bool live = f < total;
+                int p = 0;                                       // span of candidate f: the first lane with incl > f
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) {
+                    const int t = __shfl_sync(FULL, incl, p + st - 1);
+                    if (t <= f) p += st;
                 }
-                const int len = kb - ka;
-                int incl = len;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= d) incl += t;
+                const int k = f + __shfl_sync(FULL, shift, p & 31);
+                const int bd = __shfl_sync(FULL, bead, p & 31);
+                const int j = live ? S.sidx[k] : 0;
+                const float4 pj = S.pos[j];
+                const int i = bd & 0x7ff, ti = (bd >> 22) & 0xf;
+                const float4 pi = S.pos[i];
+                const int tj = __float_as_int(pj.w) & 0xff;
+                const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                bool ok = live && (r2 < cs_row[ti * ESB_MAXT + tj]) && (ESB_HALF || j != i);
+                if (ok && j < n_topo && i < n_topo) {            // only then can j be an excluded 1-2/1-3/1-4 partner
+                    const uint4 sp4 = __ldcg(reinterpret_cast<const uint4 *>(a.spec + (size_t)r * a.spec_stride + (size_t)i * ESB_MAX_SPEC));
+                    const unsigned int jj = (unsigned int)j;
+                    ok = !((sp4.x & 0xffffu) == jj || (sp4.x >> 16) == jj || (sp4.y & 0xffffu) == jj || (sp4.y >> 16) == jj ||
+                           (sp4.z & 0xffffu) == jj || (sp4.z >> 16) == jj || (sp4.w & 0xffffu) == jj || (sp4.w >> 16) == jj);
                 }
-                const int total = __shfl_sync(FULL, incl, 31);
-                const int shift = ka - (incl - len);                 // candidate f of this span sits at sorted position f + shift
-                // ---- the concatenated spans, 32 candidates per iteration ----
-                for (int f0 = 0; f0 < total; f0 += 32) {
-                    const int f = f0 + lane;
-                    const bool live = f < total;
-                    int p = 0;                                       // span of candidate f: the first lane with incl > f
-#pragma unroll
-                    for (int st = 16; st >= 1; st >>= 1) {
-                        const int t = __shfl_sync(FULL, incl, p + st - 1);
-                        if (t <= f) p += st;
-                    }
-                    const int k = f + __shfl_sync(FULL, shift, p & 31);
-                    const int j = live ? S.sidx[k] : 0;
-                    const float4 pj = S.pos[j];
-                    const int tj = __float_as_int(pj.w) & 0xff;
-                    float cs_u = 0.0f;
-                    unsigned int ent_u = 0u;
-                    if (UNIFORM) {
-                        cs_u = cs_row[ta[0] * ESB_MAXT + tj];
-                        ent_u = (unsigned int)j | ((unsigned int)tab_row[ta[0] * ESB_MAXT + tj] << (P16 ? 11 : 16));
-                    }
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const float dx = pa[b].x - pj.x, dy = pa[b].y - pj.y, dz = pa[b].z - pj.z;
-                        const float r2 = dx * dx + dy * dy + dz * dz;
-                        const float cs = UNIFORM ? cs_u : cs_row[ta[b] * ESB_MAXT + tj];
-                        bool ok = live && (r2 < cs) && (ESB_HALF ? (k > sp_[b]) : (j != ia[b]));
-                        if (TOPO) {
-                            if (ok && j < n_topo && ia[b] < n_topo) {
-                                const uint4 sp4 = __ldcg(reinterpret_cast<const uint4 *>(a.spec + (size_t)r * a.spec_stride + (size_t)ia[b] * ESB_MAX_SPEC));
-                                const unsigned int jj = (unsigned int)j;
-                                ok = !((sp4.x & 0xffffu) == jj || (sp4.x >> 16) == jj || (sp4.y & 0xffffu) == jj || (sp4.y >> 16) == jj ||
-                                       (sp4.z & 0xffffu) == jj || (sp4.z >> 16) == jj || (sp4.w & 0xffffu) == jj || (sp4.w >> 16) == jj);
-                            }
-                        }
-                        const unsigned int bits = __ballot_sync(FULL, ok);
-                        if (bits) {                                  // warp-uniform: most candidates are rejected by every bead
-                            const int at = cnt[b] + __popc(bits & lt_mask);
-                            if (ok && at < ESB_NL_MAXNB) {
-                                if (P16) pool16[(unsigned int)ia[b] * ESB_NL_STRIDE + at] =
-                                             (unsigned short)(UNIFORM ? ent_u : ((unsigned int)j | ((unsigned int)tab_row[ta[b] * ESB_MAXT + tj] << 11)));
-                                else pool[(unsigned int)ia[b] * ESB_NL_STRIDE + at] = UNIFORM ? ent_u : ((unsigned int)j | ((unsigned int)tab_row[ta[b] * ESB_MAXT + tj] << 16));
-                            }
-                            cnt[b] += __popc(bits);
-                        }
+                if (ok) {
+                    const int at = atomicAdd(&S.cnt[i], 1);
+                    if (at < ESB_NL_MAXNB) {
+                        const unsigned int tb = tab_row[ti * ESB_MAXT + tj];
+                        if (P16) pool16[(unsigned int)i * ESB_NL_STRIDE + at] = (unsigned short)((unsigned int)j | (tb << 11));
+                        else pool[(unsigned int)i * ESB_NL_STRIDE + at] = (unsigned int)j | (tb << 16);
                     }
                 }
             }
-        };
-        using T_ = std::true_type;
-        using F_ = std::false_type;
-        if (any_topo) { if (uniform) scan_spans(T_{}, T_{}); else scan_spans(T_{}, F_{}); }
-        else { if (uniform) scan_spans(F_{}, T_{}); else scan_spans(F_{}, F_{}); }
-        if (lane < 4) {
-            const int idx = 4 * q + lane;
-            int c = lane == 0 ? cnt[0] : lane == 1 ? cnt[1] : lane == 2 ? cnt[2] : cnt[3];
-            const int i = lane == 0 ? ia[0] : lane == 1 ? ia[1] : lane == 2 ? ia[2] : ia[3];
+        }
+        __syncwarp();
+        if (lane < NB) {
+            const int idx = NB * q + lane;
             if (idx < n) {
+                const int i = S.sidx[idx];
+                int c = S.cnt[i];
                 if (c > ESB_NL_MAXNB) { atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH); c = ESB_NL_MAXNB; }
                 qbuild[idx] = make_uint2((unsigned int)i * ESTRIDE, (unsigned int)i | ((unsigned int)c << 16));
                 listed += ESB_HALF ? 2 * c : c;                  // the counters report ordered pairs
@@ -548,10 +490,11 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         }
     }
     if (listed) atomicAdd(&S.misc[M_CURLIST], (int)listed);
+    ESB_BP_TICK(L_TOBS)
     __syncthreads();
 #if ESB_CLUSTER
     __threadfence();
-    csync();                                                     // the descriptors of all quads (global) are written
+    csync();                                                     // the descriptors of all batches (global) are written
 #endif
     // ---- force order: descriptors sorted by decreasing list length (counting sort on the length) ----
     if (crank() == 0) {
@@ -767,11 +710,16 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
     const int lev_lo = S.misc[M_LEVEL + lane], lev_hi = S.misc[M_LEVEL + 32 + lane];
     const int nquads = __shfl_sync(FULL, lev_hi, 31);             // (= number of items)
     int e_base = 0, e_base_next = 0;
+    // Order of the items: the chunks beyond the first of the long lists (levels >= 1), then level 0, whose quads come in
+    // order of decreasing length -- the last items handed out are the near-empty lists of the dilute species, so the
+    // warps reach the barrier behind the phase together.
+    const int n_rest = nquads - __shfl_sync(FULL, lev_lo, 0);     // items of the levels >= 1
     auto next_quad = [&]() {                                      // returns the quad of the next item, its level in e_base_next
         int t = 0;
         if (lane == 0) t = atomicAdd(&S.misc[M_QCTR], 1);
         t = __shfl_sync(FULL, t, 0);
         if (t >= nquads) return 0x7fffffff;
+        if (ESB_ITEM_ORDER) t = t < n_rest ? t + (nquads - n_rest) : t - n_rest;
         const int lev = __popc(__ballot_sync(FULL, t >= lev_lo)) + __popc(__ballot_sync(FULL, t >= lev_hi));
         e_base_next = lev * ESB_CHUNK;
         return t - (lev ? S.misc[M_LEVEL + lev - 1] : 0);

@@ -23,4 +23,4 @@ tot = (c['cyc_atom'] + c['cyc_build'] + c['cyc_force'] + c['cyc_other']).mean()
 sh = {k: c[k].mean() / tot for k in ('cyc_atom', 'cyc_build', 'cyc_force', 'cyc_other')}
 print(f'{tag:28s} R={R} {nch*200*R/dt:.3e} rs/s  pairs/eval {c["pairs"].sum()/ev/2:.0f} listed/eval {c["listed"].sum()/ev/2:.0f} '
       f'builds/chunk {c["builds"].mean()/nch:.1f} cyc/step {tot/(nch*200):.0f} atom {sh["cyc_atom"]:.3f} build {sh["cyc_build"]:.3f} '
-      f'(per build {c["cyc_build"].mean()/c["builds"].mean():.0f}) force {sh["cyc_force"]:.3f} ok {int((eng.status()==0).sum())}', flush=True)
+      f'(per build {c["cyc_build"].mean()/c["builds"].mean():.0f}) force {sh["cyc_force"]:.3f} other {sh["cyc_other"]:.3f} ok {int((eng.status()==0).sum())}', flush=True)
