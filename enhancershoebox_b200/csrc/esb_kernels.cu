@@ -57,6 +57,7 @@ struct Smem {
     unsigned short *cend;        // [-1 .. nslots + 2]  running end offset of every slot (cend[-1] = 0)
     unsigned short *sidx;        // [n_pad]       atom indices in candidate order: sorted by (slot, atom index)
     int *cnt;                    // [n_pad]       list length of every bead (first the scratch of the sort)
+    unsigned int *wtab;          // [ESB_THREADS] list build: the non-empty spans of a warp's round (own region, 32 words per warp)
     unsigned char *owner;        // [n_pad]       cluster variant: rank of the CTA that owns the bead (its force quad)
     float4 *pos_next;            // cluster variant: the other position buffer (written by the per-atom phase of all CTAs)
     unsigned short *mine;        // cluster variant: the beads this CTA owns (any order), misc[M_NMINE] of them
@@ -65,11 +66,12 @@ struct Smem {
 enum { M_QCTR = 0 /* next quad of the running build / force loop */, M_FAIL, M_PAIRS, M_CURLIST, M_FMAX /* largest |pair force| of the chunk, 2^-8 units */, M_SCAN /* one per warp */,
        M_LEVEL = M_SCAN + ESB_THREADS / 32 /* 64: work items of the force loop up to and including every chunk level (see build_lists) */,
        M_CNT_PROM = M_LEVEL + 64, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */,
+       M_CBOX = M_HIST + 52 /* list build: bounding box (6 floats) of every species class of at most 32 beads */,
 #if ESB_CLUSTER
-       M_PARITY = M_HIST + 52 /* which of the two position buffers is current */, M_NMINE /* beads this CTA owns */, M_VOTE /* rebuild vote [parity][rank] */,
+       M_PARITY = M_CBOX + 6 * ESB_NCLASS /* which of the two position buffers is current */, M_NMINE /* beads this CTA owns */, M_VOTE /* rebuild vote [parity][rank] */,
        M_CFAIL = M_VOTE + 16 /* failure bits [parity][rank] */, M_END = M_CFAIL + 16 };
 #else
-       M_END = M_HIST + 52 };
+       M_END = M_CBOX + 6 * ESB_NCLASS };
 #endif
 enum { D_RR = 0, D_PROBE = 3, D_GENE = 6,
        // per-chunk statistics, kept by thread 0 in shared memory (as 64-bit integers) instead of in registers of
@@ -86,6 +88,7 @@ __host__ __device__ inline size_t smem_bytes_for(int n_pad, int n_tables, int n_
     b += ((size_t)n_tables * sizeof(DevTab) + 15) & ~(size_t)15;
     b += ((size_t)M_END * 4 + 15) & ~(size_t)15;
     b += (size_t)D_END * 8;
+    b += (size_t)ESB_THREADS * 4;            // span table of the list build
 #if ESB_CLUSTER
     b += ((size_t)n_pad + 15) & ~(size_t)15; // bead owners
     b += (size_t)n_pad * 16;                 // second position buffer (the CTAs of a cluster write the next positions there)
@@ -117,6 +120,7 @@ __device__ __forceinline__ Smem carve(const KArgs &a, const bool first_buffer = 
     S.tab = reinterpret_cast<DevTab *>(base + o); o += ((size_t)a.n_tables * sizeof(DevTab) + 15) & ~(size_t)15;
     S.dmisc = reinterpret_cast<double *>(base + o); o += (size_t)D_END * 8;
     S.misc = reinterpret_cast<int *>(base + o); o += ((size_t)M_END * 4 + 15) & ~(size_t)15;
+    S.wtab = reinterpret_cast<unsigned int *>(base + o); o += (size_t)ESB_THREADS * 4;
     S.owner = reinterpret_cast<unsigned char *>(base + o);
 #if ESB_CLUSTER
     o += ((size_t)np + 15) & ~(size_t)15;
@@ -337,11 +341,30 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
         }
         __syncthreads();
         for (int i = tid; i < n; i += ESB_THREADS) S.cnt[i] = 0;     // (the sort scratch becomes the list lengths)
+        // a class of at most 32 beads (the gene body) is ONE span for everybody, offered only within reach of its bounding box
+        for (int B = warp; B < ESB_NCLASS; B += ESB_THREADS / 32) {
+            const int s0 = S.cend[B * nrows * ncx - 1], pop = (int)S.cend[(B + 1) * nrows * ncx - 1] - s0;
+            if (pop > 0 && pop <= 32) {
+                const float4 p = S.pos[S.sidx[s0 + min(lane, pop - 1)]];
+                float x0 = p.x, x1 = p.x, y0 = p.y, y1 = p.y, z0 = p.z, z1 = p.z;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, d)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, d));
+                    y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, d)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, d));
+                    z0 = fminf(z0, __shfl_xor_sync(0xffffffffu, z0, d)); z1 = fmaxf(z1, __shfl_xor_sync(0xffffffffu, z1, d));
+                }
+                if (lane == 0) {
+                    float *bb = reinterpret_cast<float *>(S.misc + M_CBOX + 6 * B);
+                    bb[0] = x0; bb[1] = x1; bb[2] = y0; bb[3] = y1; bb[4] = z0; bb[5] = z1;
+                }
+            }
+        }
         __syncthreads();
     }
     ESB_BP_TICK(L_TATOM)
 
     const unsigned int FULL = 0xffffffffu;
+    const unsigned int lt_mask = (1u << lane) - 1u, le_mask = 0xffffffffu >> (31 - lane);
     // P16 (at most 32 tables): 16-bit entries (neighbour | table id << 11), two per word; half the list traffic
     constexpr unsigned int ESTRIDE = P16 ? ESB_NL_STRIDE / 2 : ESB_NL_STRIDE;      // arena of a bead in words
     unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * ESTRIDE;
@@ -378,7 +401,13 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
                 const int ti = __float_as_int(pi.w) & 0xff, cls = a.class_of[ti];
                 const float c = S.setup->reach[ti * 8 + cb_class];
                 my_bead = i | (sp_i << 11) | (ti << 22) | (cls << 26);
-                if (c > 0.0f && cb_pop > 0 && (!ESB_HALF || cb_class >= cls)) {
+                if (c > 0.0f && cb_pop > 0 && cb_pop <= 32 && (!ESB_HALF || cb_class >= cls)) {
+                    // small class: the whole class as one span (rows in y = 0 marks it), when the bead is within reach of its box
+                    const float *bb = reinterpret_cast<const float *>(S.misc + M_CBOX + 6 * cb_class);
+                    const float ex = fmaxf(fmaxf(bb[0] - pi.x, pi.x - bb[1]), 0.0f), ey = fmaxf(fmaxf(bb[2] - pi.y, pi.y - bb[3]), 0.0f),
+                                ez = fmaxf(fmaxf(bb[4] - pi.z, pi.z - bb[5]), 0.0f);
+                    if (ex * ex + ey * ey + ez * ez < c * c) { nsp = 1; my_reach = c; }
+                } else if (c > 0.0f && cb_pop > 0 && (!ESB_HALF || cb_class >= cls)) {
                     const int y0 = cell_coord(pi.y - c, loy, rinv, nry), y1 = cell_coord(pi.y + c, loy, rinv, nry);
                     int z0 = cell_coord(pi.z - c, loz, rinv, nrz);
                     const int z1 = cell_coord(pi.z + c, loz, rinv, nrz);
@@ -414,23 +443,28 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
             if (sp < n_spans) {
                 const int B = c - (c / ESB_NCLASS) * ESB_NCLASS;
                 const int li = sp - cum, ny = (pack >> 8) & 0xff;
-                const int dzr = (int)(((float)li + 0.5f) * rcp_approx((float)ny));
-                const int cy = (pack & 0xff) + li - dzr * ny, cz = (pack >> 16) + dzr;
-                const float4 pi = S.pos[bead & 0x7ff];
-                // distance from the bead to the slab of the row (a little short: the row of a bead comes from a rounded product)
-                const float ylo = fmaf((float)cy, redge, loy), zlo = fmaf((float)cz, redge, loz);
-                const float dy = fmaxf(fmaxf(ylo - pi.y, pi.y - (ylo + redge)) - 1.0e-5f, 0.0f);
-                const float dz = fmaxf(fmaxf(zlo - pi.z, pi.z - (zlo + redge)) - 1.0e-5f, 0.0f);
-                const float rr = fmaf(reach, reach, -fmaf(dy, dy, dz * dz));
-                if (rr > 0.0f) {
-                    const float rx = sqrtf(rr) * 1.000001f;
-                    const int x0 = cell_coord(pi.x - rx, lox, xinv, ncx), x1 = cell_coord(pi.x + rx, lox, xinv, ncx);
-                    const int base = (B * nrows + cz * nry + cy) * ncx;
-                    ka = S.cend[base + x0 - 1];
-                    kb = S.cend[base + x1];
-                    // nothing at or before the bead itself can be listed (its own class only: later classes lie behind it anyway)
-                    if (ESB_HALF) ka = min(max(ka, ((bead >> 11) & 0x7ff) + 1), kb);
+                if (ny == 0) {                                   // small class: all of it
+                    ka = S.cend[B * nrows * ncx - 1];
+                    kb = S.cend[(B + 1) * nrows * ncx - 1];
+                } else {
+                    const int dzr = (int)(((float)li + 0.5f) * rcp_approx((float)ny));
+                    const int cy = (pack & 0xff) + li - dzr * ny, cz = (pack >> 16) + dzr;
+                    const float4 pi = S.pos[bead & 0x7ff];
+                    // distance from the bead to the slab of the row (a little short: the row of a bead comes from a rounded product)
+                    const float ylo = fmaf((float)cy, redge, loy), zlo = fmaf((float)cz, redge, loz);
+                    const float dy = fmaxf(fmaxf(ylo - pi.y, pi.y - (ylo + redge)) - 1.0e-5f, 0.0f);
+                    const float dz = fmaxf(fmaxf(zlo - pi.z, pi.z - (zlo + redge)) - 1.0e-5f, 0.0f);
+                    const float rr = fmaf(reach, reach, -fmaf(dy, dy, dz * dz));
+                    if (rr > 0.0f) {
+                        const float rx = rr * rsqrtf(rr) * 1.00001f;            // (2 ulp of MUFU.RSQ are inside the factor)
+                        const int x0 = cell_coord(pi.x - rx, lox, xinv, ncx), x1 = cell_coord(pi.x + rx, lox, xinv, ncx);
+                        const int base = (B * nrows + cz * nry + cy) * ncx;
+                        ka = S.cend[base + x0 - 1];
+                        kb = S.cend[base + x1];
+                    }
                 }
+                // nothing at or before the bead itself can be listed (its own class only: later classes lie behind it anyway)
+                if (ESB_HALF) ka = min(max(ka, ((bead >> 11) & 0x7ff) + 1), kb);
             }
             const int len = kb - ka;
             int incl = len;
@@ -440,22 +474,31 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
                 if (lane >= d) incl += t;
             }
             const int total = __shfl_sync(FULL, incl, 31);
-            const int shift = ka - (incl - len);                 // candidate f of this span sits at sorted position f + shift
-            // ---- the concatenated spans, 32 (bead, candidate) pairs per iteration ----
+            const int start = incl - len;                        // first candidate of this span in the concatenation
+            // the non-empty spans, packed, go to the warp's table: (sorted position of candidate f) - f + 65536 | atom << 17 | type << 28
+            // (a round has at most 32 n <= 65536 candidates)
+            unsigned int *wt = S.wtab + 32 * warp;
+            {
+                const unsigned int ne = __ballot_sync(FULL, len > 0);
+                __syncwarp();                                    // (the previous round's readers are done)
+                if (len > 0) wt[__popc(ne & lt_mask)] = (unsigned int)(ka - start + 65536) | ((unsigned int)(bead & 0x7ff) << 17) | ((unsigned int)((bead >> 22) & 0xf) << 28);
+                __syncwarp();
+            }
+            // ---- the concatenated spans, 32 (bead, candidate) pairs per iteration: candidate f belongs to the last span that
+            //      starts at or before f = (spans started before the window) + (starts inside the window up to f) ----
+            int before = 0;
             for (int f0 = 0; f0 < total; f0 += 32) {
                 const int f = f0 + lane;
                 const bool live = f < total;
-                int p = 0;                                       // span of candidate f: the first lane with incl > f
-#pragma unroll
-                for (int st = 16; st >= 1; st >>= 1) {
-                    const int t = __shfl_sync(FULL, incl, p + st - 1);
-                    if (t <= f) p += st;
-                }
-                const int k = f + __shfl_sync(FULL, shift, p & 31);
-                const int bd = __shfl_sync(FULL, bead, p & 31);
+                const unsigned int rel = (unsigned int)(start - f0);
+                const unsigned int starts = __reduce_or_sync(FULL, (len > 0 && rel < 32u) ? 1u << rel : 0u);
+                const unsigned int word = wt[live ? before + __popc(starts & le_mask) - 1 : 0];
+                before += __popc(starts);
+                const int k = f + (int)(word & 0x1ffffu) - 65536;
+                const int bd = (int)(word >> 17);                // atom | type << 11
                 const int j = live ? S.sidx[k] : 0;
                 const float4 pj = S.pos[j];
-                const int i = bd & 0x7ff, ti = (bd >> 22) & 0xf;
+                const int i = bd & 0x7ff, ti = bd >> 11;
                 const float4 pi = S.pos[i];
                 const int tj = __float_as_int(pj.w) & 0xff;
                 const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
