@@ -463,12 +463,15 @@ int esb_set_topology(esb_handle *h, int n_bonds, const int *bonds, int n_angles,
         if (t < 1 || t > 2) return fail(ESB_EINVAL, "bond type %d (only 1..2)", t);
         if (!add(i, j, 0, 1, t) || !add(j, i, 0, 1, t)) return fail(ESB_EINVAL, "more than %d bonded terms on one atom", ESB_MAX_TERMS);
     }
-    for (int g = 0; g < n_angles; g++) {
-        const int t = angles[4 * g], i = angles[4 * g + 1], j = angles[4 * g + 2], k = angles[4 * g + 3];
-        if (t < 1 || t > 2) return fail(ESB_EINVAL, "angle type %d (only 1..2)", t);
-        if (!add(i, j, k, 2, t) || !add(k, j, i, 2, t) || !add(j, i, k, 3, t))
-            return fail(ESB_EINVAL, "more than %d bonded terms on one atom", ESB_MAX_TERMS);
-    }
+    // a bead's row: its bonds, the angles it is the vertex of (the full-batch kernel evaluates an angle there, once),
+    // then the angles it is an end of
+    for (int pass = 0; pass < 2; pass++)
+        for (int g = 0; g < n_angles; g++) {
+            const int t = angles[4 * g], i = angles[4 * g + 1], j = angles[4 * g + 2], k = angles[4 * g + 3];
+            if (t < 1 || t > 2) return fail(ESB_EINVAL, "angle type %d (only 1..2)", t);
+            if (pass == 0 ? !add(j, i, k, 3, t) : (!add(i, j, k, 2, t) || !add(k, j, i, 2, t)))
+                return fail(ESB_EINVAL, "more than %d bonded terms on one atom", ESB_MAX_TERMS);
+        }
     // 1-2 / 1-3 / 1-4 exclusions: breadth-first to depth 3 over the bond graph
     std::vector<std::vector<int>> adj(ntp);
     for (int b = 0; b < n_bonds; b++) { adj[bonds[3 * b + 1]].push_back(bonds[3 * b + 2]); adj[bonds[3 * b + 2]].push_back(bonds[3 * b + 1]); }

@@ -622,25 +622,70 @@ __device__ __noinline__ void build_lists(const KArgs &a, const int r)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Bonded forces, one thread per bonded bead, written to S.f* before the pair loop adds to them.
-// Every bead's terms are stored kind-major (bonds, then angle ends, then the angle it is the vertex
-// of), so all threads of a warp evaluate the same kind in the same pass.
+// Bonded forces.  Like the pair forces they are accumulated in fixed point (round(f * ESB_FSCALE) per component and
+// term): every term is evaluated ONCE -- a bond by its end of lower index, an angle by its vertex -- and the shares of
+// the other beads are scattered with the same shared-memory integer atomics into the same accumulators (round 2
+// evaluated every term from every bead it touches: 5 evaluations per polymer bead instead of 2).  The cluster variant
+// still does that (a bead's force lives with its owner CTA) but with the same two functions below, whose results are
+// exact mirror images between the two ends of a term: every variant adds up the same integers.
+// A bead's row holds its bonds, then the angle it is the vertex of, then the angles it is an end of.
 // [LAMMPS-ext] BondHarmonic::compute  E = K (r - r0)^2       (bond_coeff, run_single_shoebox.py:632-633)
 // [LAMMPS-ext] AngleCosine::compute   E = K (1 + cos theta)  (angle_coeff, run_single_shoebox.py:583-584)
 // ------------------------------------------------------------------------------------------------
-template <bool ENERGY>
+struct I3 { int x, y, z; };
+// r^2 with a fixed operation order: the soft-phase force depends on its last bit, and every kernel variant must agree
+__device__ __forceinline__ float dist_sq(const float dx, const float dy, const float dz) { return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))); }
+// share of the bead at p of its bond with the bead at q (the other end gets the exact negative: dx -> -dx, r^2 unchanged).
+// (reciprocal square roots, MUFU.RSQ, ~2 ulp, instead of sqrt and divisions; the bonded forces stay within 1e-6 of the fp64 oracle's)
+__device__ __forceinline__ I3 bond_share(const float4 p, const float4 q, const float r0, const float K, float &e)
+{
+    const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+    const float r2 = dist_sq(dx, dy, dz);
+    const float ri = rsqrtf(r2);
+    const float dr = __fsub_rn(__fmul_rn(r2, ri), r0);
+    const float rk = __fmul_rn(K, dr);
+    e = __fmul_rn(rk, dr);
+    const float fs = (r2 > 0.0f) ? __fmul_rn(__fmul_rn(-2.0f * ESB_FSCALE, rk), ri) : 0.0f;
+    I3 o; o.x = __float2int_rn(__fmul_rn(dx, fs)); o.y = __float2int_rn(__fmul_rn(dy, fs)); o.z = __float2int_rn(__fmul_rn(dz, fs));
+    return o;
+}
+// share of the END bead at p1 of the angle p1 - pv - p3 (vertex pv); the other end's share is the same function with the
+// ends exchanged (every intermediate that both calls need -- cos theta, 1/(r1 r2) -- is symmetric in the exchange bit for
+// bit), the vertex gets minus the sum of the two
+__device__ __forceinline__ I3 angle_end_share(const float4 p1, const float4 pv, const float4 p3, const float K, float &c_out)
+{
+    const float d1x = __fsub_rn(p1.x, pv.x), d1y = __fsub_rn(p1.y, pv.y), d1z = __fsub_rn(p1.z, pv.z);
+    const float d2x = __fsub_rn(p3.x, pv.x), d2y = __fsub_rn(p3.y, pv.y), d2z = __fsub_rn(p3.z, pv.z);
+    const float ri1 = rsqrtf(dist_sq(d1x, d1y, d1z)), ri2 = rsqrtf(dist_sq(d2x, d2y, d2z)), ri12 = __fmul_rn(ri1, ri2);
+    float c = __fmul_rn(__fmaf_rn(d1z, d2z, __fmaf_rn(d1y, d2y, __fmul_rn(d1x, d2x))), ri12);
+    c = fminf(fmaxf(c, -1.0f), 1.0f);
+    c_out = c;
+    const float a11 = __fmul_rn(__fmul_rn(K * ESB_FSCALE, c), __fmul_rn(ri1, ri1)), a12 = -__fmul_rn(K * ESB_FSCALE, ri12);
+    I3 o;
+    o.x = __float2int_rn(__fmaf_rn(a11, d1x, __fmul_rn(a12, d2x)));
+    o.y = __float2int_rn(__fmaf_rn(a11, d1y, __fmul_rn(a12, d2y)));
+    o.z = __float2int_rn(__fmaf_rn(a11, d1z, __fmul_rn(a12, d2z)));
+    return o;
+}
+template <int NP> __device__ __forceinline__ unsigned int force_off(const KArgs &a);
+template <int NP> __device__ __forceinline__ void red_add3(const KArgs &a, const unsigned int addr, const int vx, const int vy, const int vz);
+
+template <int NP, bool ENERGY>
 __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, const int r, const float r0_1, const float r0_2,
                                               double &e_bond, double &e_angle)
 {
-    const int n = a.n_atoms, n_topo = a.n_topo, ntp = a.n_topo_pad;
+    const int n_topo = a.n_topo, ntp = a.n_topo_pad;
     const uint2 *bterm = a.bterm + (size_t)r * a.bterm_stride;     // per replica when the actin topology is dynamic
+#if ESB_HALF
+    const unsigned int fbase = smem_base() + force_off<NP>(a);
+#endif
 #if ESB_CLUSTER
     for (int k = threadIdx.x; k < S.misc[M_NMINE]; k += ESB_THREADS) {   // the other beads belong to other CTAs of the cluster
         const int i = S.mine[k];
 #else
     for (int i = threadIdx.x; i < n_topo; i += ESB_THREADS) {
 #endif
-        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        int fx = 0, fy = 0, fz = 0;
         if (i < n_topo) {
             const float4 pi = S.pos[i];
 #pragma unroll 1
@@ -649,52 +694,51 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
                 const uint2 term = a.bterm_stride ? __ldcg(&bterm[(size_t)t * ntp + i]) : bterm[(size_t)t * ntp + i];
                 const int kind = term.y & 0xff, type = (term.y >> 8) & 0xff;
                 if (kind == 0) break;                                         // a bead's terms are stored without gaps
-                const float4 pa = S.pos[term.x & 0xffffu];
-                // (reciprocal square roots, MUFU.RSQ, ~2 ulp, instead of sqrt and three divisions per term: a third of the
-                // phase's instructions; the bonded forces stay within 1e-6 of the fp64 oracle's)
+                const int ja = (int)(term.x & 0xffffu);
+                const float4 pa = S.pos[ja];
+                float e;
                 if (kind == 1) {
-                    const float dx = pi.x - pa.x, dy = pi.y - pa.y, dz = pi.z - pa.z;
-                    const float r2b = dx * dx + dy * dy + dz * dz;
-                    const float ri = rsqrtf(r2b);
-                    const float rr = r2b * ri;
-                    const float dr = rr - (type == 1 ? r0_1 : r0_2);
-                    const float rk = a.bond_k[type] * dr;
-                    const float fb = (r2b > 0.0f) ? -2.0f * rk * ri : 0.0f;
-                    fx += dx * fb; fy += dy * fb; fz += dz * fb;
-                    if (ENERGY) e_bond += 0.5 * (double)(rk * dr);   // each bond is visited from both ends
+#if ESB_HALF
+                    if (ja < i) continue;                                     // the other end evaluates this bond
+#endif
+                    const I3 s = bond_share(pi, pa, type == 1 ? r0_1 : r0_2, a.bond_k[type], e);
+                    fx += s.x; fy += s.y; fz += s.z;
+#if ESB_HALF
+                    red_add3<NP>(a, fbase + 4u * (unsigned int)ja, -s.x, -s.y, -s.z);
+                    if (ENERGY) e_bond += (double)e;
+#else
+                    if (ENERGY) e_bond += 0.5 * (double)e;                    // each bond is visited from both ends
+#endif
                     continue;
                 }
-                const float4 pb = S.pos[term.x >> 16];
+#if ESB_HALF
+                if (kind == 2) break;                                         // angles are evaluated by their vertex (the end rows come last)
+#endif
+                const int jb = (int)(term.x >> 16);
+                const float4 pb = S.pos[jb];
                 const float k = a.angle_k[type];
                 if (kind == 2) {
                     // this bead is an end (i1); pa = vertex (i2), pb = other end (i3)
-                    const float d1x = pi.x - pa.x, d1y = pi.y - pa.y, d1z = pi.z - pa.z;
-                    const float d2x = pb.x - pa.x, d2y = pb.y - pa.y, d2z = pb.z - pa.z;
-                    const float rsq1 = d1x * d1x + d1y * d1y + d1z * d1z, rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
-                    const float ri1 = rsqrtf(rsq1), ri2 = rsqrtf(rsq2), ri12 = ri1 * ri2;
-                    float c = (d1x * d2x + d1y * d2y + d1z * d2z) * ri12;
-                    c = fminf(fmaxf(c, -1.0f), 1.0f);
-                    const float a11 = k * c * (ri1 * ri1), a12 = -k * ri12;
-                    fx += a11 * d1x + a12 * d2x; fy += a11 * d1y + a12 * d2y; fz += a11 * d1z + a12 * d2z;
+                    const I3 s = angle_end_share(pi, pa, pb, k, e);
+                    fx += s.x; fy += s.y; fz += s.z;
                 } else {
                     // this bead is the vertex (i2); pa = i1, pb = i3
-                    const float d1x = pa.x - pi.x, d1y = pa.y - pi.y, d1z = pa.z - pi.z;
-                    const float d2x = pb.x - pi.x, d2y = pb.y - pi.y, d2z = pb.z - pi.z;
-                    const float rsq1 = d1x * d1x + d1y * d1y + d1z * d1z, rsq2 = d2x * d2x + d2y * d2y + d2z * d2z;
-                    const float ri1 = rsqrtf(rsq1), ri2 = rsqrtf(rsq2), ri12 = ri1 * ri2;
-                    float c = (d1x * d2x + d1y * d2y + d1z * d2z) * ri12;
-                    c = fminf(fmaxf(c, -1.0f), 1.0f);
-                    const float a11 = k * c * (ri1 * ri1), a12 = -k * ri12, a22 = k * c * (ri2 * ri2);
-                    fx -= (a11 * d1x + a12 * d2x) + (a22 * d2x + a12 * d1x);
-                    fy -= (a11 * d1y + a12 * d2y) + (a22 * d2y + a12 * d1y);
-                    fz -= (a11 * d1z + a12 * d2z) + (a22 * d2z + a12 * d1z);
-                    if (ENERGY) e_angle += (double)(k * (1.0f + c));
+                    const I3 s1 = angle_end_share(pa, pi, pb, k, e), s3 = angle_end_share(pb, pi, pa, k, e);
+                    fx -= s1.x + s3.x; fy -= s1.y + s3.y; fz -= s1.z + s3.z;
+#if ESB_HALF
+                    red_add3<NP>(a, fbase + 4u * (unsigned int)ja, s1.x, s1.y, s1.z);
+                    red_add3<NP>(a, fbase + 4u * (unsigned int)jb, s3.x, s3.y, s3.z);
+#endif
+                    if (ENERGY) e_angle += (double)(k * (1.0f + e));
                 }
             }
+#if ESB_HALF
+            red_add3<NP>(a, fbase + 4u * (unsigned int)i, fx, fy, fz);
+#else
+            S.gx[i] = __int_as_float(fx); S.gy[i] = __int_as_float(fy); S.gz[i] = __int_as_float(fz);
+#endif
         }
-        if (i < n_topo) { S.gx[i] = fx; S.gy[i] = fy; S.gz[i] = fz; }
     }
-    (void)n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -715,9 +759,6 @@ __device__ __forceinline__ float lds32f(const unsigned int addr)
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
-// r^2 with a fixed operation order: the soft-phase force depends on its last bit, and every kernel variant must agree
-__device__ __forceinline__ float dist_sq(const float dx, const float dy, const float dz) { return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))); }
-
 template <int NP, int MODE, bool ENERGY, bool P16>
 __device__ __noinline__ void force_phase(const KArgs &a, const int r, const float soft_a, const float r0_1, const float r0_2,
                                          double *energy /* [3] pair, bond, angle: per-thread partials (ENERGY only) */)
@@ -730,7 +771,7 @@ __device__ __noinline__ void force_phase(const KArgs &a, const int r, const floa
     double e_pair = 0.0, e_bond = 0.0, e_angle = 0.0;
     // no barrier between the two: the bonded pass writes S.g*, the pair loop S.f*; a warp whose beads have no
     // bonded terms starts on the quads while the others wait for their term rows.  (S.misc[M_QCTR] is 0 on entry.)
-    bonded_forces<ENERGY>(S, a, r, r0_1, r0_2, e_bond, e_angle);
+    bonded_forces<NP, ENERGY>(S, a, r, r0_1, r0_2, e_bond, e_angle);
     const unsigned int *pool = a.nl_pool + (size_t)r * a.n_pad * (P16 ? ESB_NL_STRIDE / 2 : ESB_NL_STRIDE);
     const uint2 *qinfo = a.nl_qinfo + (size_t)r * 2 * a.n_pad;
 #if ESB_CLUSTER
@@ -979,10 +1020,10 @@ __device__ __noinline__ int atom_phase(const KArgs &a, const bool do_final, cons
         float vx = S.vx[i], vy = S.vy[i], vz = S.vz[i];
         const bool topo = i < a.n_topo;
         // bonded + pair (fixed point -> fp32; the accumulators go back to zero for the next evaluation)
-        const int ifx = __float_as_int(S.fx[i]), ify = __float_as_int(S.fy[i]), ifz = __float_as_int(S.fz[i]);
+        int ifx = __float_as_int(S.fx[i]), ify = __float_as_int(S.fy[i]), ifz = __float_as_int(S.fz[i]);
         if (ESB_HALF) { S.fx[i] = 0.0f; S.fy[i] = 0.0f; S.fz[i] = 0.0f; }
-        float fx = (topo ? S.gx[i] : 0.0f) + (float)ifx * inv_fscale, fy = (topo ? S.gy[i] : 0.0f) + (float)ify * inv_fscale,
-              fz = (topo ? S.gz[i] : 0.0f) + (float)ifz * inv_fscale;
+        else if (topo) { ifx += __float_as_int(S.gx[i]); ify += __float_as_int(S.gy[i]); ifz += __float_as_int(S.gz[i]); }   // (cluster variant: the bonded shares have their own arrays)
+        float fx = (float)ifx * inv_fscale, fy = (float)ify * inv_fscale, fz = (float)ifz * inv_fscale;
         int fail = post_force<false>(a, i, p, vx, vy, vz, fx, fy, fz, k0, k1, eval, dummy);
         const unsigned int iabs = max(max((unsigned int)abs(ifx), (unsigned int)abs(ify)), (unsigned int)abs(ifz));
         if (ESB_FGUARD && iabs > 0x40000000u) fail |= ESB_ST_NONFINITE;      // the pair force left half the fixed-point range
@@ -1436,7 +1477,7 @@ __device__ __noinline__ void actin_events(const KArgs &a, const int r, const esb
         L[0] = (unsigned short)nfree; L[1] = (unsigned short)nfil;
     }
     __syncthreads();
-    // ---- bonds, angles and exclusions of the actin beads from their links (kind-major, no gaps) ----
+    // ---- bonds, angles and exclusions of the actin beads from their links (bonds, vertex, ends; no gaps) ----
     if (d.actin_flags & 1) {
         uint2 *bt = a.bterm + (size_t)r * a.bterm_stride;
         unsigned short *sp = a.spec + (size_t)r * a.spec_stride;
@@ -1451,9 +1492,9 @@ __device__ __noinline__ void actin_events(const KArgs &a, const int r, const esb
             auto add = [&](unsigned int x, unsigned int y, int kind) { bt[(size_t)nt * ntp + b] = make_uint2(x | (y << 16), (unsigned int)kind | (2u << 8)); nt++; };
             if (p1 != NO) add(p1, 0u, 1);
             if (m1 != NO) add(m1, 0u, 1);
+            if (p1 != NO && m1 != NO) add(p1, m1, 3);
             if (p2 != NO) add(p1, p2, 2);
             if (m2 != NO) add(m1, m2, 2);
-            if (p1 != NO && m1 != NO) add(p1, m1, 3);
             for (; nt < ESB_MAX_TERMS; nt++) bt[(size_t)nt * ntp + b] = make_uint2(0u, 0u);
             unsigned short *row = sp + (size_t)b * ESB_MAX_SPEC;
             row[0] = (unsigned short)p1; row[1] = (unsigned short)p2; row[2] = (unsigned short)p3;
@@ -1750,16 +1791,16 @@ esb_forces_kernel(const __grid_constant__ KArgs a, const int pair_mode, const in
     else if (pair_mode == 2) force_phase<NP, 2, true, false>(a, r, 0.0f, (float)rs.r0[1], (float)rs.r0[2], en);
     else {
         double eb = 0.0, ea = 0.0;
-        bonded_forces<true>(S, a, r, (float)rs.r0[1], (float)rs.r0[2], eb, ea); en[1] = eb; en[2] = ea;
         for (int k = tid; k < np; k += ESB_THREADS) { S.fx[k] = 0.0f; S.fy[k] = 0.0f; S.fz[k] = 0.0f; }
+        __syncthreads();
+        bonded_forces<NP, true>(S, a, r, (float)rs.r0[1], (float)rs.r0[2], eb, ea); en[1] = eb; en[2] = ea;
     }
     __syncthreads();
     double e_wall = 0.0;
     for (int i = tid; i < a.n_atoms; i += ESB_THREADS) {
         const bool topo = i < a.n_topo;
         const float inv_fscale = 1.0f / ESB_FSCALE;
-        float fx = (topo ? S.gx[i] : 0.0f) + (float)__float_as_int(S.fx[i]) * inv_fscale, fy = (topo ? S.gy[i] : 0.0f) + (float)__float_as_int(S.fy[i]) * inv_fscale,
-              fz = (topo ? S.gz[i] : 0.0f) + (float)__float_as_int(S.fz[i]) * inv_fscale;
+        float fx = (float)__float_as_int(S.fx[i]) * inv_fscale, fy = (float)__float_as_int(S.fy[i]) * inv_fscale, fz = (float)__float_as_int(S.fz[i]) * inv_fscale;
         if (with_post) {
             const int fail = post_force<true>(a, i, S.pos[i], S.vx[i], S.vy[i], S.vz[i], fx, fy, fz, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), eval, e_wall);
             if (fail) atomicOr(&S.misc[M_FAIL], fail);
