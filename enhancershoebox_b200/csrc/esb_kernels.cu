@@ -202,7 +202,7 @@ __device__ __forceinline__ float4 lds128(const unsigned int addr)
 // ten times the median).  Level c = the c-th chunk of every quad that has one; the lengths are sorted, so level c is the
 // first Q_c quads and item t is found from the running sums of Q_c.
 #ifndef ESB_ITEM_ROUNDS
-#define ESB_ITEM_ROUNDS 16
+#define ESB_ITEM_ROUNDS 32
 #endif
 #define ESB_CHUNK (ESB_ITEM_ROUNDS * ESB_G)      // entries of one bead per item
 #ifndef ESB_CUT32
