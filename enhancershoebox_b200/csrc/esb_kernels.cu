@@ -81,11 +81,12 @@ enum { M_QCTR = 0 /* next quad of the running build / force loop */, M_FAIL, M_P
        M_LEVEL = M_SCAN + ESB_THREADS / 32 /* 64: work items of the force loop up to and including every chunk level (see build_lists) */,
        M_CNT_PROM = M_LEVEL + 64, M_CNT_GENE, M_NRNP, M_NRBP, M_HIST /* 49 */,
        M_CBOX = M_HIST + 52 /* list build: bounding box (6 floats) of every species class of at most 32 beads */,
+       M_CROW = M_CBOX + 6 * ESB_NCLASS /* list build: occupied rows of every class, first y | last y << 8 | first z << 16 | last z << 24 */,
 #if ESB_CLUSTER
-       M_PARITY = M_CBOX + 6 * ESB_NCLASS /* which of the two position buffers is current */, M_NMINE /* beads this CTA owns */, M_VOTE /* rebuild vote [parity][rank] */,
+       M_PARITY = M_CROW + ESB_NCLASS /* which of the two position buffers is current */, M_NMINE /* beads this CTA owns */, M_VOTE /* rebuild vote [parity][rank] */,
        M_CFAIL = M_VOTE + 16 /* failure bits [parity][rank] */, M_END = M_CFAIL + 16 };
 #else
-       M_END = M_CBOX + 6 * ESB_NCLASS };
+       M_END = M_CROW + ESB_NCLASS };
 #endif
 enum { D_RR = 0, D_PROBE = 3, D_GENE = 6,
        // per-chunk statistics, kept by thread 0 in shared memory (as 64-bit integers) instead of in registers of
@@ -210,6 +211,9 @@ __device__ __forceinline__ float4 lds128(const unsigned int addr)
 #endif
 #ifndef ESB_ITEM_ORDER
 #define ESB_ITEM_ORDER 1
+#endif
+#ifndef ESB_BUILD_NB
+#define ESB_BUILD_NB 5
 #endif
 #ifndef ESB_FGUARD
 #define ESB_FGUARD 1
@@ -356,8 +360,21 @@ __device__ ESB_PHASE_B void build_lists(const KArgs &a, const int r)
         __syncthreads();
         for (int i = tid; i < n; i += ESB_THREADS) S.cnt[i] = 0;     // (the sort scratch becomes the list lengths)
         // a class of at most 32 beads (the gene body) is ONE span for everybody, offered only within reach of its bounding box
+        // and nobody looks for a class outside the rows it occupies (the Ser5P cluster sits in a few of them)
         for (int B = warp; B < ESB_NCLASS; B += ESB_THREADS / 32) {
             const int s0 = S.cend[B * nrows * ncx - 1], pop = (int)S.cend[(B + 1) * nrows * ncx - 1] - s0;
+            {
+                int ya = 255, yb = 0, za = 255, zb = 0;
+                for (int rw = lane; rw < nrows; rw += 32) {
+                    if ((int)S.cend[(B * nrows + rw + 1) * ncx - 1] > (int)S.cend[(B * nrows + rw) * ncx - 1]) {
+                        const int rz = rw / nry, ry = rw - rz * nry;
+                        ya = min(ya, ry); yb = max(yb, ry); za = min(za, rz); zb = max(zb, rz);
+                    }
+                }
+                ya = __reduce_min_sync(0xffffffffu, ya); yb = __reduce_max_sync(0xffffffffu, yb);
+                za = __reduce_min_sync(0xffffffffu, za); zb = __reduce_max_sync(0xffffffffu, zb);
+                if (lane == 0) S.misc[M_CROW + B] = ya | (yb << 8) | (za << 16) | (zb << 24);
+            }
             if (pop > 0 && pop <= 32) {
                 const float4 p = S.pos[S.sidx[s0 + min(lane, pop - 1)]];
                 float x0 = p.x, x1 = p.x, y0 = p.y, y1 = p.y, z0 = p.z, z1 = p.z;
@@ -389,13 +406,16 @@ __device__ ESB_PHASE_B void build_lists(const KArgs &a, const int r)
     const float *cs_row = S.setup->cutsq_skin;
     const unsigned char *tab_row = S.setup->tabid;
     unsigned int listed = 0;
-    constexpr int NB = 4;                                            // beads per batch: NB * ESB_NCLASS (bead, class) combinations <= 32 lanes
+    constexpr int NB = ESB_BUILD_NB;                                 // beads per batch: NB * ESB_NCLASS (bead, class) combinations <= 32 lanes
     static_assert(NB * ESB_NCLASS <= 32, "one lane per (bead, class) combination");
     const int nbatch = (n + NB - 1) / NB;
     // this lane's (bead, class) combination of a batch
     const int cb_bead = lane / ESB_NCLASS, cb_class = lane - cb_bead * ESB_NCLASS;
-    int cb_pop = 0;                                                  // beads of class cb_class
-    if (lane < NB * ESB_NCLASS) cb_pop = (int)S.cend[(cb_class + 1) * nrows * ncx - 1] - (int)S.cend[cb_class * nrows * ncx - 1];
+    int cb_pop = 0, cb_rows = 0;                                     // beads of class cb_class, the rows it occupies
+    if (lane < NB * ESB_NCLASS) {
+        cb_pop = (int)S.cend[(cb_class + 1) * nrows * ncx - 1] - (int)S.cend[cb_class * nrows * ncx - 1];
+        cb_rows = S.misc[M_CROW + cb_class];
+    }
     for (;;) {
         // batches are handed out dynamically: their cost varies by two orders of magnitude with the species
         int q = 0;
@@ -422,14 +442,16 @@ __device__ ESB_PHASE_B void build_lists(const KArgs &a, const int r)
                                 ez = fmaxf(fmaxf(bb[4] - pi.z, pi.z - bb[5]), 0.0f);
                     if (ex * ex + ey * ey + ez * ez < c * c) { nsp = 1; my_reach = c; }
                 } else if (c > 0.0f && cb_pop > 0 && (!ESB_HALF || cb_class >= cls)) {
-                    const int y0 = cell_coord(pi.y - c, loy, rinv, nry), y1 = cell_coord(pi.y + c, loy, rinv, nry);
-                    int z0 = cell_coord(pi.z - c, loz, rinv, nrz);
-                    const int z1 = cell_coord(pi.z + c, loz, rinv, nrz);
+                    const int y0 = max(cell_coord(pi.y - c, loy, rinv, nry), cb_rows & 0xff), y1 = min(cell_coord(pi.y + c, loy, rinv, nry), (cb_rows >> 8) & 0xff);
+                    int z0 = max(cell_coord(pi.z - c, loz, rinv, nrz), (cb_rows >> 16) & 0xff);
+                    const int z1 = min(cell_coord(pi.z + c, loz, rinv, nrz), (cb_rows >> 24) & 0xff);
                     // HALF list: in the bead's own class nothing before its own z row comes after it in candidate order
                     if (ESB_HALF && cb_class == cls) z0 = max(z0, cell_coord(pi.z, loz, rinv, nrz));
-                    my_pack = y0 | ((y1 - y0 + 1) << 8) | (z0 << 16);
-                    my_reach = c;
-                    nsp = (y1 - y0 + 1) * (z1 - z0 + 1);
+                    if (y1 >= y0 && z1 >= z0) {
+                        my_pack = y0 | ((y1 - y0 + 1) << 8) | (z0 << 16);
+                        my_reach = c;
+                        nsp = (y1 - y0 + 1) * (z1 - z0 + 1);
+                    }
                 }
             }
             my_end = nsp;

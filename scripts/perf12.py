@@ -16,7 +16,10 @@ plans = P.chunk_schedule('genes_stages', n_chunks=1000 + nch + 2)[1000:]
 eng.set_schedule(plans=plans, observe=True)
 eng.run(0, 2)
 eng.reset_counters()
-t0 = time.time(); eng.run(2, nch); dt = time.time() - t0
+dt = 1e9
+for rep in range(2):          # best of two (the first launch of a process runs on a cold device)
+    eng.reset_counters()
+    t0 = time.time(); eng.run(2, nch); dt = min(dt, time.time() - t0)
 c = eng.counters()
 ev = c['evals'].sum()
 tot = (c['cyc_atom'] + c['cyc_build'] + c['cyc_force'] + c['cyc_other']).mean()
