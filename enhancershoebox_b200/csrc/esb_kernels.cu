@@ -879,7 +879,8 @@ __device__ ESB_PHASE_F void force_phase(const KArgs &a, const int r, const float
         auto pair_body = [&](const unsigned int ent, const int e) {
             if (e < cnt) {
                 const float4 pj = lds128(sb + 16u * (ent & (P16 ? 0x7ffu : 0xffffu)));
-                const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                // half list: the difference points to bead j, whose share goes out as it is; bead i's is its exact negative
+                const float dx = ESB_HALF ? pj.x - pi.x : pi.x - pj.x, dy = ESB_HALF ? pj.y - pi.y : pi.y - pj.y, dz = ESB_HALF ? pj.z - pi.z : pi.z - pj.z;
                 const float r2 = dist_sq(dx, dy, dz);
                 float fpair;
                 if (MODE == 1) {
@@ -934,8 +935,10 @@ __device__ ESB_PHASE_F void force_phase(const KArgs &a, const int r, const float
                 // same integers whether a pair is visited once (half list + scatter) or from both sides (full list)
                 const float fs = fpair * ESB_FSCALE;
                 const int ix = __float2int_rn(dx * fs), iy = __float2int_rn(dy * fs), iz = __float2int_rn(dz * fs);
-                fx += ix; fy += iy; fz += iz;
-                if (ESB_HALF) red_add3<NP>(a, fbase + 4u * (ent & (P16 ? 0x7ffu : 0xffffu)), -ix, -iy, -iz);
+                if (ESB_HALF) {
+                    fx -= ix; fy -= iy; fz -= iz;
+                    red_add3<NP>(a, fbase + 4u * (ent & (P16 ? 0x7ffu : 0xffffu)), ix, iy, iz);
+                } else { fx += ix; fy += iy; fz += iz; }
             }
         };
         constexpr int DEPTH = ESB_PREFETCH;                       // list words in flight per lane
