@@ -214,7 +214,7 @@ int rebuild_setups(esb_handle *h)
         DevTab d;
         memset(&d, 0, sizeof(d));
         d.innersq = T.innersq; d.invdelta = 1.0 / T.delta; d.delta = (float)T.delta; d.invdelta_f = (float)(1.0 / T.delta);
-        d.innersq_f = (float)T.innersq;
+        d.xoff_f = (float)(T.innersq / T.delta);
         d.patch = 0u;                                  // empty closed-form range: every bin from the array
         d.cutsq = nextafterf((float)(T.cut * T.cut * (1.0 + 2e-7)), INFINITY);
         d.K = 0.0f; d.is6 = 0.0f; d.c = 1.0f;

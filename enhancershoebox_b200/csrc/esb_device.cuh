@@ -51,7 +51,7 @@ struct __align__(16) DevTab {
     float cutsq;                // effective cutoff^2: beyond it every bin value is 0
     float invdelta_f;           // fp32 bin-index estimate (verified against the bin edges, see force_phase)
     float delta;
-    float innersq_f;
+    float xoff_f;               // innersq * invdelta: the bin estimate is r2 * invdelta_f - xoff_f
     float K;                    // 24 eps_eff / s^6
     float is6;                  // 1 / s^6
     float c;                    // alpha (1-lam)^2

@@ -898,17 +898,20 @@ __device__ ESB_PHASE_F void force_phase(const KArgs &a, const int r, const float
                     const unsigned int T4 = tbase + 48u * tb;                         // DevTab = 3 float4 words
 #if ESB_CUT32
                     if (!(r2 < lds32f(T4))) return;                                   // cutsq (one word: a quarter of the wavefronts of the full row)
-                    const float4 t0 = lds128(T4);                                     // cutsq, invdelta_f, delta, innersq_f
+                    const float4 t0 = lds128(T4);                                     // cutsq, invdelta_f, delta, xoff_f
 #else
-                    const float4 t0 = lds128(T4);                                     // cutsq, invdelta_f, delta, innersq_f
+                    const float4 t0 = lds128(T4);                                     // cutsq, invdelta_f, delta, xoff_f
                     if (!(r2 < t0.x)) return;
 #endif
                     const float4 t1 = lds128(T4 + 16u);                               // K, is6, c, patch
-                    const float u = (r2 - t0.w) * t0.y;
+                    // bin estimate u = w - X with w = r2 * invdelta, X = innersq * invdelta (t0.w).  |u - u_exact| <= 5.4e-7 w:
+                    // r2 carries 3e-7 relative (differences 2^-24 each, squares and sums), the scale, its product, X and the
+                    // subtraction 2^-24 of at most w each -- relative to w, NOT to u: the offset amplifies the error of r2
+                    const float w = r2 * t0.y;
+                    const float u = w - t0.w;
                     int it = (int)u;
                     const float frac = u - (float)it;
-                    // |u - u_exact| <= 8 ulp-relative (dx: 1, squares+sums: 5, offset+scale: 2) = 4.8e-7 u
-                    const float margin = fmaf(u, 5.0e-7f, 1.0e-4f);
+                    const float margin = fmaf(w, 5.5e-7f, 1.0e-6f);
                     if (!(frac > margin && frac < 1.0f - margin)) {
                         const float4 t2f = lds128(T4 + 32u);
                         const double2 t2 = make_double2(__hiloint2double(__float_as_int(t2f.y), __float_as_int(t2f.x)), __hiloint2double(__float_as_int(t2f.w), __float_as_int(t2f.z)));
@@ -921,8 +924,8 @@ __device__ ESB_PHASE_F void force_phase(const KArgs &a, const int r, const float
                     }
                     const unsigned int patch = __float_as_uint(t1.w);            // p0hi | (plo - p0hi) << 16
                     const bool closed = (unsigned int)(it - (int)(patch & 0xffffu)) < (patch >> 16);
-                    // closed form at the bin midpoint (bins [p0hi, plo) lie below rc)
-                    const float qm = fmaf((float)it + 0.5f, t0.z, t0.w);
+                    // closed form at the bin midpoint innersq + (it + 1/2) delta = (it + 1/2 + X) delta (bins [p0hi, plo) lie below rc)
+                    const float qm = (((float)it + 0.5f) + t0.w) * t0.z;
                     const float q2 = qm * qm;
                     const float x = fmaf(q2 * qm, t1.y, t1.z);
                     const float inv = rcp_approx(x);                                // <= 1 ulp: 3 ulp on inv^3, far inside the 1e-5 parity bound
