@@ -5,7 +5,8 @@ oracle_ensemble_box11_2000.npz = 48 x 2000 chunks, the production run length
 (box 11, promoter 3, -x 20, -a 100; made by tests/golden/make_oracle_ensemble.py).  The device runs
 192 replicas of the same protocol with different seeds.  Window means must agree within 4.5
 standard errors of the difference (both ensembles contribute); quantities fixed by the protocol
-(RNP count, frame times) must agree exactly."""
+(RNP count, frame times) must agree exactly.  Replicas that fail on the way (about 1 in 1000 production runs does) are
+dropped, as the reference's launcher drops and repeats them."""
 import os
 
 import numpy as np
@@ -34,9 +35,15 @@ def test_ensemble_matches_oracle(fixture, windows):
     eng = E.ShoeboxBatch(datas, seeds=np.arange(R) + 777, thresholds=thr, activations=act)
     eng.set_schedule(nch, observe=True)
     eng.run()
-    assert np.all(eng.status() == 0) and np.all(z["status"] == 0)
-    fr = eng.frames()
-    x, v, t = eng.state()
+    # A production run fails now and then ("Pair distance < table inner cutoff" after a type change inside the cluster:
+    # 5-7 of 6600 runs in the committed 330-cell sweeps, profiles/r2_reference_ensemble_all*.md) and the reference's
+    # launcher deletes and re-runs such a run (run_parallel_shoebox.sh:1-14): failed replicas are left out here, and
+    # there must be few of them.
+    ok = eng.status() == 0
+    assert (~ok).sum() <= max(1, R // 100) and np.all(z["status"] == 0), eng.status()[~ok]
+    fr = eng.frames()[ok]
+    x, v, t = (q[ok] for q in eng.state())
+    R = int(ok.sum())
     # exact, protocol-determined quantities
     assert np.array_equal(fr[:, :, 0], np.tile((np.arange(nch) + 1) * 6.0, (R, 1)))
     assert np.all((t == 5).sum(axis=1) == z["nrnp"][0, -1])
