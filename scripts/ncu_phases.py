@@ -13,6 +13,7 @@ ANCHORS = [  # (phase, first line containing this string); a phase runs to the n
     ('build:candidates', 'the concatenated spans, 32 (bead, candidate) pairs'),
     ('build:descriptors', '__syncwarp();\n        if (lane < NB)'),
     ('build:tail', 'force order: descriptors sorted by decreasing list length'),
+    ('bonded', '// Bonded forces.  Like the pair forces'),
     ('bonded', 'void bonded_forces('),
     ('force:setup+items', 'void force_phase('),
     ('force:pair_body', 'auto pair_body = [&]'),
