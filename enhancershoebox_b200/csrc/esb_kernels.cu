@@ -497,6 +497,10 @@ __device__ ESB_PHASE_B void build_lists(const KArgs &a, const int r)
                         const int base = (B * nrows + cz * nry + cy) * ncx;
                         ka = S.cend[base + x0 - 1];
                         kb = S.cend[base + x1];
+#if defined(ESB_BUILD_CHECK) && ESB_BUILD_CHECK          // self-check build (compute-sanitizer is not available on the pool): index ranges of the span
+                        if (B < 0 || B >= ESB_NCLASS || cy < 0 || cy >= nry || cz < 0 || cz >= nrz || x0 < 0 || x1 >= ncx || x0 > x1 || base + x1 >= nslots || ka > kb || kb > n)
+                            atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH);
+#endif
                     }
                 }
                 // nothing at or before the bead itself can be listed (its own class only: later classes lie behind it anyway)
@@ -532,6 +536,9 @@ __device__ ESB_PHASE_B void build_lists(const KArgs &a, const int r)
                 before += __popc(starts);
                 const int k = f + (int)(word & 0x1ffffu) - 65536;
                 const int bd = (int)(word >> 17);                // atom | type << 11
+#if defined(ESB_BUILD_CHECK) && ESB_BUILD_CHECK
+                if (live && (k < 0 || k >= n || (bd & 0x7ff) >= n || (ESB_HALF && k <= 0))) atomicOr(&S.misc[M_FAIL], ESB_ST_NEIGH);
+#endif
                 const int j = live ? S.sidx[k] : 0;
                 const float4 pj = S.pos[j];
                 const int i = bd & 0x7ff, ti = bd >> 11;
