@@ -212,6 +212,9 @@ __device__ __forceinline__ float4 lds128(const unsigned int addr)
 #ifndef ESB_ITEM_ORDER
 #define ESB_ITEM_ORDER 1
 #endif
+#ifndef ESB_ITEM_FAST
+#define ESB_ITEM_FAST 1
+#endif
 #ifndef ESB_BUILD_NB
 #define ESB_BUILD_NB 5
 #endif
@@ -846,8 +849,12 @@ __device__ ESB_PHASE_F void force_phase(const KArgs &a, const int r, const float
         if (lane == 0) t = atomicAdd(&S.misc[M_QCTR], 1);
         t = __shfl_sync(FULL, t, 0);
         if (t >= nquads) return 0x7fffffff;
-        if (ESB_ITEM_ORDER) t = t < n_rest ? t + (nquads - n_rest) : t - n_rest;
-        const int lev = __popc(__ballot_sync(FULL, t >= lev_lo)) + __popc(__ballot_sync(FULL, t >= lev_hi));
+        if (ESB_ITEM_ORDER) {
+            if (ESB_ITEM_FAST && t >= n_rest) { e_base_next = 0; return t - n_rest; }     // level 0 (nearly every item): nothing to decode
+            t = t < n_rest ? t + (nquads - n_rest) : t - n_rest;
+        }
+        // (lists have at most ESB_NL_MAXNB entries: with chunks of 64 and more the levels 32..63 do not exist)
+        const int lev = __popc(__ballot_sync(FULL, t >= lev_lo)) + (32 * ESB_CHUNK > ESB_NL_MAXNB ? 0 : __popc(__ballot_sync(FULL, t >= lev_hi)));
         e_base_next = lev * ESB_CHUNK;
         return t - (lev ? S.misc[M_LEVEL + lev - 1] : 0);
     };
@@ -980,7 +987,7 @@ __device__ ESB_PHASE_F void force_phase(const KArgs &a, const int r, const float
             }
         }
 #pragma unroll
-        for (int d = ESB_G >> 1; d >= 1; d >>= 1) {
+        for (int d = ESB_G >> 1; d >= 1; d >>= 1) {                // (every lane issuing its own atomics instead: -1 %)
             fx += __shfl_xor_sync(FULL, fx, d);
             fy += __shfl_xor_sync(FULL, fy, d);
             fz += __shfl_xor_sync(FULL, fz, d);
