@@ -1,4 +1,5 @@
-"""The committed device ensembles (profiles/r2_reference_ensemble_*.json, written on a B200 by
+"""The committed device ensembles (profiles/r2_reference_ensemble_*.json and, with the final round-2 kernel,
+r3_reference_ensemble_*.json, written on a B200 by
 scripts/reference_ensemble.py) against the reference's own LAMMPS sweep -- the same comparison as
 tests/test_gpu_reference_ensemble.py, re-checkable without a GPU -- and the known answers of the golden table."""
 import glob
@@ -24,7 +25,7 @@ def test_golden_table_known_answers():
         assert np.allclose(q, np.round(q), atol=1e-6)
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_reference_ensemble_*.json"))))
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r[23]_reference_ensemble_*.json"))))
 def test_committed_device_ensembles_match_the_reference(path):
     """Stated tolerances.  Cells with the reference's own 100 repeats: |z| < 4 per comparison.  The 330-cell sweeps at 20
     repeats per cell (heavy-tailed per-run distributions, small samples): |z| < 6.5, at most 3 % of the comparisons beyond
