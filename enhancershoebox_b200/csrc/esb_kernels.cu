@@ -212,9 +212,6 @@ __device__ __forceinline__ float4 lds128(const unsigned int addr)
 #ifndef ESB_ITEM_ORDER
 #define ESB_ITEM_ORDER 1
 #endif
-#ifndef ESB_TICKET_AHEAD
-#define ESB_TICKET_AHEAD 1
-#endif
 #ifndef ESB_ITEM_FAST
 #define ESB_ITEM_FAST 1
 #endif
@@ -847,19 +844,10 @@ __device__ ESB_PHASE_F void force_phase(const KArgs &a, const int r, const float
     // order of decreasing length -- the last items handed out are the near-empty lists of the dilute species, so the
     // warps reach the barrier behind the phase together.
     const int n_rest = nquads - __shfl_sync(FULL, lev_lo, 0);     // items of the levels >= 1
-    // The ticket of an item is drawn one item ahead of its use (lane 0 holds it): the shared-memory atomic's round trip
-    // overlaps the item in between instead of stalling the warp at the top of every item.
-    int ticket = 0;
-    if (ESB_TICKET_AHEAD && lane == 0) ticket = atomicAdd(&S.misc[M_QCTR], 1);
     auto next_quad = [&]() {                                      // returns the quad of the next item, its level in e_base_next
         int t = 0;
-        if (ESB_TICKET_AHEAD) {
-            t = __shfl_sync(FULL, ticket, 0);
-            if (lane == 0 && t < nquads) ticket = atomicAdd(&S.misc[M_QCTR], 1);
-        } else {
-            if (lane == 0) t = atomicAdd(&S.misc[M_QCTR], 1);
-            t = __shfl_sync(FULL, t, 0);
-        }
+        if (lane == 0) t = atomicAdd(&S.misc[M_QCTR], 1);         // (drawing the ticket one item ahead of its use: -4 %, the live ticket costs spills)
+        t = __shfl_sync(FULL, t, 0);
         if (t >= nquads) return 0x7fffffff;
         if (ESB_ITEM_ORDER) {
             if (ESB_ITEM_FAST && t >= n_rest) { e_base_next = 0; return t - n_rest; }     // level 0 (nearly every item): nothing to decode
