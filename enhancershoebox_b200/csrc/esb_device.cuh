@@ -1,8 +1,9 @@
 // esb_device.cuh -- device-side data layout and helpers shared by the kernels of libesb.so.
 //
 // One CTA owns one replica: positions (+type), velocities, forces and the positions of the last
-// neighbour build live in shared memory for a whole chunk; the neighbour list (full list, u32 entries =
-// partner index | table id << 16) lives in per-bead arenas of a per-replica global pool.  See DESIGN.md.
+// neighbour build live in shared memory for a whole chunk; the neighbour list (half list of 16-bit entries = partner
+// index | table id << 11 with at most 32 tables, u32 entries otherwise; full list in the cluster variant) lives in
+// per-bead arenas of a per-replica global pool.  See DESIGN.md.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,7 +35,7 @@
 #endif
                                      // overflow it (LAMMPS: neigh_modify one 10000 page 100000, run_single_shoebox.py:533)
 #ifndef ESB_BUILD_REVERSE
-#define ESB_BUILD_REVERSE 0              // 1: hand out the build's quads last class first (paid with the full list of round 1; -0.7 % with the half list)
+#define ESB_BUILD_REVERSE 0              // 1: hand out the build's batches last class first (paid with the full list of round 1; -1 % with the half list)
 #endif
 #define ESB_NCLASS 6                 // species classes for the row sort: chromatin-like, actin, RBP, RNP, Ser5P, gene body (induced/active)
 #define ESB_N_COUNTERS 12             // per replica: evals, builds, pairs, listed, steps, total_active, cycles in atom/build/force/observe phases, dangerous builds, max |pair force| * 256

@@ -4,13 +4,14 @@
 //                     memory); work items = (replica, chunk[, segment]) from a ticket counter.  Per chunk:
 //                     set-up force evaluation + n_steps x {integrate, (re)build list, forces}, then the per-chunk
 //                     measurements / gene state machine / frame record, the actin events and the synthetic-
-//                     microscopy voxel counts.  This file is compiled twice (ESB_TAG 512 / 1024: CTA size).
+//                     microscopy voxel counts.  This file is compiled three times (ESB_TAG 512 / 1024: CTA size; 2048: clusters).
 // esb_forces_kernel   parity hook: one force evaluation (+ energies) at the stored positions.
 // esb_pack/unpack     double <-> float4 state conversion for the host-facing ABI.
 //
 // The kernels are templates on the bead capacity NP (n_pad) so that every shared-memory array
-// offset is an immediate; the phases are separate __noinline__ functions (each gets the full
-// register budget) that take the __grid_constant__ kernel arguments by reference.
+// offset is an immediate; the phases are functions that take the __grid_constant__ kernel arguments by reference:
+// the force and the per-atom phase are inlined into the kernel, the list build, the observation and the actin events
+// are __noinline__ (ESB_PHASE_INLINE).
 // Reference semantics (what each phase stands in for) are cited at the device functions.
 #include <type_traits>
 
