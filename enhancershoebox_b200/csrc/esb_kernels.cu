@@ -589,16 +589,19 @@ __device__ ESB_PHASE_B void build_lists(const KArgs &a, const int r)
     // ---- force order: descriptors sorted by decreasing list length (counting sort on the length) ----
     if (crank() == 0) {
         uint2 *qforce = a.nl_qinfo + (size_t)r * 2 * a.n_pad;
-        int *hist = reinterpret_cast<int *>(S.fx);                 // 2048 counters; the scratch is free again
-        for (int k = tid; k < ESB_NL_MAXNB + 1; k += ESB_THREADS) hist[k] = 0;
+        // one counter per possible length 0 .. hmax: a list cannot be longer than the system has beads (nor than an arena),
+        // so the counters fit the scratch -- free again -- of a system of any size
+        const int hmax = min(ESB_NL_MAXNB, n);
+        int *hist = reinterpret_cast<int *>(S.fx);
+        for (int k = tid; k < hmax + 1; k += ESB_THREADS) hist[k] = 0;
         __syncthreads();
-        for (int k = tid; k < n; k += ESB_THREADS) atomicAdd(&hist[ESB_NL_MAXNB - (int)(__ldcg(&qbuild[k]).y >> 16)], 1);
+        for (int k = tid; k < n; k += ESB_THREADS) atomicAdd(&hist[hmax - (int)(__ldcg(&qbuild[k]).y >> 16)], 1);
         __syncthreads();
-        // exclusive scan of the 2048 counters: an equal share per thread
+        // exclusive scan of the counters: an equal share per thread
         constexpr int PER = (ESB_NL_MAXNB + ESB_THREADS) / ESB_THREADS;
         int v[PER], s = 0;
 #pragma unroll
-        for (int k = 0; k < PER; k++) { v[k] = (PER * tid + k <= ESB_NL_MAXNB) ? hist[PER * tid + k] : 0; s += v[k]; }
+        for (int k = 0; k < PER; k++) { v[k] = (PER * tid + k <= hmax) ? hist[PER * tid + k] : 0; s += v[k]; }
         int incl = s;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -610,13 +613,13 @@ __device__ ESB_PHASE_B void build_lists(const KArgs &a, const int r)
         int base = incl - s;
         for (int w = 0; w < warp; w++) base += S.misc[M_SCAN + w];
 #pragma unroll
-        for (int k = 0; k < PER; k++) { if (PER * tid + k <= ESB_NL_MAXNB) hist[PER * tid + k] = base; base += v[k]; }
+        for (int k = 0; k < PER; k++) { if (PER * tid + k <= hmax) hist[PER * tid + k] = base; base += v[k]; }
         __syncthreads();
 #if ESB_HALF
-        // hist[ESB_NL_MAXNB - L] = beads with a list longer than L = the beads of chunk level L / ESB_CHUNK
+        // hist[hmax - L] = beads with a list longer than L = the beads of chunk level L / ESB_CHUNK
         if (tid < 64) {
             const int L = tid * ESB_CHUNK;
-            const int beads = L <= ESB_NL_MAXNB ? hist[ESB_NL_MAXNB - L] : 0;
+            const int beads = L <= hmax ? hist[hmax - L] : 0;
             S.misc[M_LEVEL + tid] = (beads + 32 / ESB_G - 1) / (32 / ESB_G);       // quads of this level
         }
         __syncthreads();
@@ -634,7 +637,7 @@ __device__ ESB_PHASE_B void build_lists(const KArgs &a, const int r)
 #endif
         for (int k = tid; k < n; k += ESB_THREADS) {
             const uint2 d = __ldcg(&qbuild[k]);
-            const int at = atomicAdd(&hist[ESB_NL_MAXNB - (int)(d.y >> 16)], 1);
+            const int at = atomicAdd(&hist[hmax - (int)(d.y >> 16)], 1);
             qforce[at] = d;
 #if ESB_CLUSTER
             // the CTA that takes force quad at/4 owns the bead: bonded terms, pair loop, integration
