@@ -197,6 +197,13 @@ __device__ __forceinline__ float4 lds128(const unsigned int addr)
 // pair contributes at most ~365.  A bead whose sum leaves half the range (16384) flags the replica (ESB_ST_NONFINITE)
 // in the per-atom phase; counter 11 reports the largest sum seen.
 #define ESB_FSCALE 0x1p16f
+// Bonded shares have their own accumulators (S.g*) at a coarser scale, 2^12 counts per force unit: resolution 2.4e-4 (five
+// terms per bead: <= 6e-4, 1e-5 of the Langevin noise amplitude), range +-524288.  The actin filaments need the range: fix
+// s3 re-ramps their bond r0 from 0.033 in every run (run_single_shoebox.py:638-639), bonds pass through lengths of ~1e-3
+// and the cosine-angle force K / r reaches 1e4..1e5 for a step -- survivable in the reference's doubles and in fp32, but
+// beyond the +-16384 at which a 2^16 accumulator is flagged (with the bonded shares in the pair accumulators 59 of 64
+// configs[1] repeats were flagged by chunk 400 instead of the 20 that die of a wall crossing).
+#define ESB_BSCALE 0x1p12f
 // Work items of the half-list force loop: a quad (32 / ESB_G beads, consecutive in the order of decreasing list length) times a
 // CHUNK of its lists, ESB_ITEM_ROUNDS entries per lane.  A bead whose list is longer than a chunk is finished by other
 // warps: every item adds its part of bead i's force with the same integer atomics that reach bead j, so the items are
@@ -241,6 +248,13 @@ __device__ __forceinline__ void red_add3(const KArgs &a, const unsigned int addr
         asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr + st), "r"(vy) : "memory");
         asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr + 2u * st), "r"(vz) : "memory");
     }
+}
+// the same for arrays of a run-time stride (the bonded accumulators, [n_topo_pad] each)
+__device__ __forceinline__ void red_add3s(const unsigned int addr, const unsigned int stride_bytes, const int vx, const int vy, const int vz)
+{
+    asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr), "r"(vx) : "memory");
+    asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr + stride_bytes), "r"(vy) : "memory");
+    asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr + 2u * stride_bytes), "r"(vz) : "memory");
 }
 template <int NP>
 __device__ __forceinline__ int tab_off4(const KArgs &a)
@@ -695,7 +709,7 @@ __device__ __forceinline__ I3 bond_share(const float4 p, const float4 q, const f
     const float dr = __fsub_rn(__fmul_rn(r2, ri), r0);
     const float rk = __fmul_rn(K, dr);
     e = __fmul_rn(rk, dr);
-    const float fs = (r2 > 0.0f) ? __fmul_rn(__fmul_rn(-2.0f * ESB_FSCALE, rk), ri) : 0.0f;
+    const float fs = (r2 > 0.0f) ? __fmul_rn(__fmul_rn(-2.0f * ESB_BSCALE, rk), ri) : 0.0f;
     I3 o; o.x = __float2int_rn(__fmul_rn(dx, fs)); o.y = __float2int_rn(__fmul_rn(dy, fs)); o.z = __float2int_rn(__fmul_rn(dz, fs));
     return o;
 }
@@ -710,7 +724,7 @@ __device__ __forceinline__ I3 angle_end_share(const float4 p1, const float4 pv, 
     float c = __fmul_rn(__fmaf_rn(d1z, d2z, __fmaf_rn(d1y, d2y, __fmul_rn(d1x, d2x))), ri12);
     c = fminf(fmaxf(c, -1.0f), 1.0f);
     c_out = c;
-    const float a11 = __fmul_rn(__fmul_rn(K * ESB_FSCALE, c), __fmul_rn(ri1, ri1)), a12 = -__fmul_rn(K * ESB_FSCALE, ri12);
+    const float a11 = __fmul_rn(__fmul_rn(K * ESB_BSCALE, c), __fmul_rn(ri1, ri1)), a12 = -__fmul_rn(K * ESB_BSCALE, ri12);
     I3 o;
     o.x = __float2int_rn(__fmaf_rn(a11, d1x, __fmul_rn(a12, d2x)));
     o.y = __float2int_rn(__fmaf_rn(a11, d1y, __fmul_rn(a12, d2y)));
@@ -727,7 +741,7 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
     const int n_topo = a.n_topo, ntp = a.n_topo_pad;
     const uint2 *bterm = a.bterm + (size_t)r * a.bterm_stride;     // per replica when the actin topology is dynamic
 #if ESB_HALF
-    const unsigned int fbase = smem_base() + force_off<NP>(a);
+    const unsigned int gbase = smem_base() + (unsigned int)(reinterpret_cast<unsigned char *>(S.gx) - smem_raw), gstride = 4u * (unsigned int)ntp;
 #endif
 #if ESB_CLUSTER
     for (int k = threadIdx.x; k < S.misc[M_NMINE]; k += ESB_THREADS) {   // the other beads belong to other CTAs of the cluster
@@ -754,7 +768,7 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
                     const I3 s = bond_share(pi, pa, type == 1 ? r0_1 : r0_2, a.bond_k[type], e);
                     fx += s.x; fy += s.y; fz += s.z;
 #if ESB_HALF
-                    red_add3<NP>(a, fbase + 4u * (unsigned int)ja, -s.x, -s.y, -s.z);
+                    red_add3s(gbase + 4u * (unsigned int)ja, gstride, -s.x, -s.y, -s.z);
                     if (ENERGY) e_bond += (double)e;
 #else
                     if (ENERGY) e_bond += 0.5 * (double)e;                    // each bond is visited from both ends
@@ -776,14 +790,14 @@ __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, con
                     const I3 s1 = angle_end_share(pa, pi, pb, k, e), s3 = angle_end_share(pb, pi, pa, k, e);
                     fx -= s1.x + s3.x; fy -= s1.y + s3.y; fz -= s1.z + s3.z;
 #if ESB_HALF
-                    red_add3<NP>(a, fbase + 4u * (unsigned int)ja, s1.x, s1.y, s1.z);
-                    red_add3<NP>(a, fbase + 4u * (unsigned int)jb, s3.x, s3.y, s3.z);
+                    red_add3s(gbase + 4u * (unsigned int)ja, gstride, s1.x, s1.y, s1.z);
+                    red_add3s(gbase + 4u * (unsigned int)jb, gstride, s3.x, s3.y, s3.z);
 #endif
                     if (ENERGY) e_angle += (double)(k * (1.0f + e));
                 }
             }
 #if ESB_HALF
-            red_add3<NP>(a, fbase + 4u * (unsigned int)i, fx, fy, fz);
+            red_add3s(gbase + 4u * (unsigned int)i, gstride, fx, fy, fz);
 #else
             S.gx[i] = __int_as_float(fx); S.gy[i] = __int_as_float(fy); S.gz[i] = __int_as_float(fz);
 #endif
@@ -1080,13 +1094,19 @@ __device__ ESB_PHASE_F int atom_phase(const KArgs &a, const bool do_final, const
         float vx = S.vx[i], vy = S.vy[i], vz = S.vz[i];
         const bool topo = i < a.n_topo;
         // bonded + pair (fixed point -> fp32; the accumulators go back to zero for the next evaluation)
-        int ifx = __float_as_int(S.fx[i]), ify = __float_as_int(S.fy[i]), ifz = __float_as_int(S.fz[i]);
+        const int ifx = __float_as_int(S.fx[i]), ify = __float_as_int(S.fy[i]), ifz = __float_as_int(S.fz[i]);
         if (ESB_HALF) { S.fx[i] = 0.0f; S.fy[i] = 0.0f; S.fz[i] = 0.0f; }
-        else if (topo) { ifx += __float_as_int(S.gx[i]); ify += __float_as_int(S.gy[i]); ifz += __float_as_int(S.gz[i]); }   // (cluster variant: the bonded shares have their own arrays)
         float fx = (float)ifx * inv_fscale, fy = (float)ify * inv_fscale, fz = (float)ifz * inv_fscale;
+        unsigned int gabs = 0u;
+        if (topo) {                                                  // bonded shares: own accumulators, ESB_BSCALE
+            const int igx = __float_as_int(S.gx[i]), igy = __float_as_int(S.gy[i]), igz = __float_as_int(S.gz[i]);
+            if (ESB_HALF) { S.gx[i] = 0.0f; S.gy[i] = 0.0f; S.gz[i] = 0.0f; }
+            fx += (float)igx * (1.0f / ESB_BSCALE); fy += (float)igy * (1.0f / ESB_BSCALE); fz += (float)igz * (1.0f / ESB_BSCALE);
+            gabs = max(max((unsigned int)abs(igx), (unsigned int)abs(igy)), (unsigned int)abs(igz));
+        }
         int fail = post_force<false>(a, i, p, vx, vy, vz, fx, fy, fz, k0, k1, eval, dummy);
         const unsigned int iabs = max(max((unsigned int)abs(ifx), (unsigned int)abs(ify)), (unsigned int)abs(ifz));
-        if (ESB_FGUARD && iabs > 0x40000000u) fail |= ESB_ST_NONFINITE;      // the pair force left half the fixed-point range
+        if (ESB_FGUARD && max(iabs, gabs) > 0x40000000u) fail |= ESB_ST_NONFINITE;      // a force sum left half the fixed-point range
         fmax_seen = max(fmax_seen, iabs);
         if (fail) atomicOr(&S.misc[M_FAIL], fail);
         if (do_final) { vx += dtf * fx; vy += dtf * fy; vz += dtf * fz; }
@@ -1673,6 +1693,7 @@ esb_run_kernel(const __grid_constant__ KArgs a, const int chunk_begin, const int
             S.vx[k] = v.x; S.vy[k] = v.y; S.vz[k] = v.z;
             S.fx[k] = 0.0f; S.fy[k] = 0.0f; S.fz[k] = 0.0f;       // (a segment that continues a chunk starts without a build)
         }
+        if (ESB_HALF) for (int k = tid; k < 3 * a.n_topo_pad; k += ESB_THREADS) S.gx[k] = 0.0f;     // bonded accumulators (gx, gy, gz are contiguous)
         for (int k = tid; k < M_END; k += ESB_THREADS)
             S.misc[k] = (SEG && it0 > 0 && k == M_CURLIST) ? rs.curlist
                         : (SEG && ESB_HALF && it0 > 0 && k >= M_LEVEL && k < M_LEVEL + 64) ? __ldcg(&a.nl_levels[(size_t)r * 64 + (k - M_LEVEL)]) : 0;
@@ -1839,6 +1860,7 @@ esb_forces_kernel(const __grid_constant__ KArgs a, const int pair_mode, const in
     for (int k = tid; k < a.n_tables * (int)(sizeof(DevTab) / 4); k += ESB_THREADS)
         reinterpret_cast<int *>(S.tab)[k] = reinterpret_cast<const int *>(a.tabs)[k];
     for (int k = tid; k < M_END; k += ESB_THREADS) S.misc[k] = 0;
+    for (int k = tid; k < 3 * a.n_topo_pad; k += ESB_THREADS) S.gx[k] = 0.0f;
     {
         const int *src = reinterpret_cast<const int *>(a.setups + setup_id);
         int *dst = reinterpret_cast<int *>(S.setup);
@@ -1861,6 +1883,10 @@ esb_forces_kernel(const __grid_constant__ KArgs a, const int pair_mode, const in
         const bool topo = i < a.n_topo;
         const float inv_fscale = 1.0f / ESB_FSCALE;
         float fx = (float)__float_as_int(S.fx[i]) * inv_fscale, fy = (float)__float_as_int(S.fy[i]) * inv_fscale, fz = (float)__float_as_int(S.fz[i]) * inv_fscale;
+        if (topo) {
+            fx += (float)__float_as_int(S.gx[i]) * (1.0f / ESB_BSCALE); fy += (float)__float_as_int(S.gy[i]) * (1.0f / ESB_BSCALE);
+            fz += (float)__float_as_int(S.gz[i]) * (1.0f / ESB_BSCALE);
+        }
         if (with_post) {
             const int fail = post_force<true>(a, i, S.pos[i], S.vx[i], S.vy[i], S.vz[i], fx, fy, fz, (uint32_t)rs.seed, (uint32_t)(rs.seed >> 32), eval, e_wall);
             if (fail) atomicOr(&S.misc[M_FAIL], fail);

@@ -61,7 +61,7 @@ def test_post_force_langevin_walls_anchors(eng, orc, snapshots, tag, pair, box11
     assert abs(eg[0][3] - eo[3]) <= 2e-6 * abs(eo[3]) + 1e-6
 
 
-def test_bin_index_is_exact(eng, orc, snapshots):
+def test_bin_index_is_exact(eng, orc, snapshots, box11):
     """The LOOKUP bin of every pair is the oracle's: with array lookups the only difference left is
     fp32 rounding of the table values and of the accumulation (<< one bin step of ~1e-4 relative)."""
     x, v, t = _load(snapshots, "1999")
@@ -72,8 +72,13 @@ def test_bin_index_is_exact(eng, orc, snapshots):
     fg, _ = eng.forces("B", use_arrays=True)
     # one flipped bin on a strongly repulsive pair (F ~ 50, neighbouring bins differ by ~1e-4 relative)
     # would show up as ~4e-5 of the largest force; fp32 table values and the fixed-point accumulation (2^-16 per
-    # pair and component, ~60 pairs per bead: ~1e-4 absolute at worst) stay below 3e-6
-    assert np.abs(fg[0] - fo).max() / np.abs(fo).max() < 3e-6
+    # pair and component, ~60 pairs per bead: ~1e-4 absolute at worst) stay below 3e-6 on the beads without bonded
+    # terms (most pairs have such a bead: RBP, RNP, Ser5P); the polymer beads add the rounding of their bonded shares
+    # (2^-12 per term and component, <= 5 terms: 6e-4 absolute at worst) and stay below 2e-5
+    bonded = np.zeros(len(x), bool)
+    bonded[np.unique(box11.bonds[:, 1:])] = True
+    err = np.abs(fg[0] - fo).max(axis=1) / np.abs(fo).max()
+    assert err[~bonded].max() < 3e-6 and err[bonded].max() < 2e-5, (err[~bonded].max(), err[bonded].max())
 
 
 def test_pairs_excluded_and_counted(eng, orc, snapshots, box11):
