@@ -250,7 +250,7 @@ __device__ __forceinline__ void red_add3(const KArgs &a, const unsigned int addr
     }
 }
 // the same for arrays of a run-time stride (the bonded accumulators, [n_topo_pad] each)
-__device__ __forceinline__ void red_add3s(const unsigned int addr, const unsigned int stride_bytes, const int vx, const int vy, const int vz)
+[[maybe_unused]] __device__ __forceinline__ void red_add3s(const unsigned int addr, const unsigned int stride_bytes, const int vx, const int vy, const int vz)
 {
     asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr), "r"(vx) : "memory");
     asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr + stride_bytes), "r"(vy) : "memory");
@@ -686,10 +686,10 @@ __device__ ESB_PHASE_B void build_lists(const KArgs &a, const int r)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Bonded forces.  Like the pair forces they are accumulated in fixed point (round(f * ESB_FSCALE) per component and
+// Bonded forces.  Like the pair forces they are accumulated in fixed point (round(f * ESB_BSCALE) per component and
 // term): every term is evaluated ONCE -- a bond by its end of lower index, an angle by its vertex -- and the shares of
-// the other beads are scattered with the same shared-memory integer atomics into the same accumulators (round 2
-// evaluated every term from every bead it touches: 5 evaluations per polymer bead instead of 2).  The cluster variant
+// the other beads are scattered with the same shared-memory integer atomics, into accumulators of their own (S.g*; the
+// first round-2 kernel evaluated every term from every bead it touches: 5 evaluations per polymer bead instead of 2).  The cluster variant
 // still does that (a bead's force lives with its owner CTA) but with the same two functions below, whose results are
 // exact mirror images between the two ends of a term: every variant adds up the same integers.
 // A bead's row holds its bonds, then the angle it is the vertex of, then the angles it is an end of.
@@ -731,8 +731,6 @@ __device__ __forceinline__ I3 angle_end_share(const float4 p1, const float4 pv, 
     o.z = __float2int_rn(__fmaf_rn(a11, d1z, __fmul_rn(a12, d2z)));
     return o;
 }
-template <int NP> __device__ __forceinline__ unsigned int force_off(const KArgs &a);
-template <int NP> __device__ __forceinline__ void red_add3(const KArgs &a, const unsigned int addr, const int vx, const int vy, const int vz);
 
 template <int NP, bool ENERGY>
 __device__ __forceinline__ void bonded_forces(const Smem &S, const KArgs &a, const int r, const float r0_1, const float r0_2,
