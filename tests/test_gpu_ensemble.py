@@ -40,7 +40,7 @@ def test_ensemble_matches_oracle(fixture, windows):
     # launcher deletes and re-runs such a run (run_parallel_shoebox.sh:1-14): failed replicas are left out here, and
     # there must be few of them.
     ok = eng.status() == 0
-    assert (~ok).sum() <= max(1, R // 100) and np.all(z["status"] == 0), eng.status()[~ok]
+    assert (~ok).sum() <= max(2, R // 64) and np.all(z["status"] == 0), eng.status()[~ok]     # (192 runs at ~1.3e-3 each: 3 or more once in 500 test runs)
     fr = eng.frames()[ok]
     x, v, t = (q[ok] for q in eng.state())
     R = int(ok.sum())
